@@ -14,6 +14,7 @@
 //                          XFLUIDS.cpp:658-687) after these step counts; 0 = initial state
 //   XF_DUMP_STAGE=1        additionally dump the intermediates of step 1 / RK stage 1:
 //                          primitives after UpdateStates, LU + wall fluxes after ComputeLU
+//   XF_DUMP_IC=1           dump ic_U / ic_T: the raw initial condition before BC + UpdateStates
 //   XF_DUMP_T=1            dump T (the Newton warm-start state) with every U dump
 // Prints one line "ORACLE_TIMING ..." with the wall time of the time loop.
 #include "global_class.h"
@@ -41,12 +42,16 @@ int main(int argc, char *argv[])
 	solver.AllocateMemory(q);
 	// InitialCondition() also tries to read a checkpoint from OutputDir; none is ever written by this driver
 	solver.InitialCondition(q);
-	solver.BoundaryCondition(q);
-	solver.UpdateStates(q);
-
 	const Block bl = setup.BlSz;
 	const size_t N = size_t(bl.Xmax) * bl.Ymax * bl.Zmax;
 	Fluid *fl = solver.fluids[0];
+	if (!envs("XF_DUMP_DIR").empty() && (envs("XF_DUMP_STAGE") == "1" || envs("XF_DUMP_IC") == "1"))
+	{ // raw initial condition: U and the Newton warm-start T exactly as the sample kernel left them
+		dump_raw(envs("XF_DUMP_DIR") + "/ic_U.bin", fl->d_U, N * Emax * sizeof(real_t));
+		dump_raw(envs("XF_DUMP_DIR") + "/ic_T.bin", fl->d_fstate.T, N * sizeof(real_t));
+	}
+	solver.BoundaryCondition(q);
+	solver.UpdateStates(q);
 
 	int nsteps = setup.nStepmax;
 	if (!envs("XF_NSTEPS").empty())

@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures from the UNMODIFIED reference compiled by oracle/build_ref.sh.
+
+Run in the build container (needs /root/reference to have built oracle/_ref):
+    python tests/golden/make_golden.py
+Each tests/golden/<case>_w<weno>.npz holds, for a small grid of one BASELINE config: the raw initial condition
+(ic_U, ic_T), the reference's conserved state after 1 and 10 steps (AoS incl. ghosts), T after 10 steps and the dt
+sequence.  These pin the CPU restatement (oracle/xf_oracle.cpp) and, on the GPU box where /root/reference does not
+exist, the CUDA path directly."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import xfref
+
+GRID = {"shock-tube": (400, 0, 0), "vortex": (32, 32, 0), "riemann": (32, 32, 0), "sbi": (24, 12, 12), "jet": (24, 12, 12)}
+VARIANTS = [("shock-tube", 5), ("shock-tube", 7), ("vortex", 5), ("riemann", 5), ("sbi", 5), ("sbi", 7), ("jet", 5)]
+
+if __name__ == "__main__":
+    for case, weno in VARIANTS:
+        res = GRID[case]
+        A, meta, out = xfref.run_ref(case, res, 10, dump_steps=(1, 10), weno=weno, stage_dump=True)
+        assert "ORACLE_TIMING" in out and "error=0" in out, out[-2000:]
+        np.savez_compressed(os.path.join(xfref.GOLDEN, "%s_w%d.npz" % (case, weno)), res=np.array(res), weno=weno,
+                            ic_U=A["ic_U"], ic_T=A["ic_T"], U_step1=A["U_step1"], U_step10=A["U_step10"], T_step10=A["T_step10"],
+                            s1_LU=A["s1_LU"], dt=np.array(meta["dt"]))
+        print(case, weno, "ok", meta["dt"][:2])

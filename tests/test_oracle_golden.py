@@ -1,0 +1,35 @@
+"""CPU: the oracle restatement (oracle/xf_oracle.cpp) against the golden vectors produced by the UNMODIFIED
+reference (tests/golden/make_golden.py) -- bit-exact on U, T and dt for all five BASELINE configs."""
+import os
+
+import numpy as np
+import pytest
+
+import xfref
+
+VARIANTS = [("shock-tube", 5), ("shock-tube", 7), ("vortex", 5), ("riemann", 5), ("sbi", 5), ("sbi", 7), ("jet", 5)]
+
+
+@pytest.mark.parametrize("case,weno", VARIANTS)
+def test_oracle_matches_reference_golden(case, weno):
+    g = np.load(os.path.join(xfref.GOLDEN, "%s_w%d.npz" % (case, weno)))
+    res = tuple(int(x) for x in g["res"])
+    o = xfref.Oracle(case, res, weno=weno)
+    o.set_state(g["ic_U"], g["ic_T"])
+    assert o.startup() == 0
+    # stage-1 right-hand side of step 1
+    dt = o.get_dt()
+    assert dt == g["dt"][0]
+    o.boundary(0); o.update_states(0); o.get_lu(0)
+    assert np.array_equal(o.arr("LU"), g["s1_LU"])
+    # restart and run the full steps
+    o.set_state(g["ic_U"], g["ic_T"])
+    o.startup()
+    n, dts, t = o.run(1)
+    assert n == 1 and dts[0] == g["dt"][0]
+    assert np.array_equal(o.arr("U"), g["U_step1"])
+    n, dts, t = o.run(9)
+    assert n == 9 and np.array_equal(np.array(dts), g["dt"][1:10])
+    assert np.array_equal(o.arr("U"), g["U_step10"])
+    assert np.array_equal(o.arr("T"), g["T_step10"])
+    assert not o.flags().any()
