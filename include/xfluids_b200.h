@@ -1,0 +1,153 @@
+/* xfluids_b200.h -- C ABI of the B200-native XFluids inviscid-RHS engine (libxfluids_b200.so).
+ *
+ * The reference has no plugin/FFI layer; its de-facto seam is the set of host "block" functions
+ * that class Fluid forwards to (reference src/Fluids.cpp:585-588,897-961), which take POD structs
+ * and raw device pointers.  Every entry point below replaces one of them and cites it.  All
+ * functions return 0 on success or a negative xf_status; no exceptions cross this boundary, no
+ * torch / C++ types appear in it.
+ *
+ * Data layout on the device (DESIGN.md "Data layout"): structure-of-arrays, FP64,
+ *     field[n][k][j][i]  at  d_field[n * xf_field_stride(ctx) + (k*Ymax + j)*xf_pitch(ctx) + i]
+ * with the x pitch padded to a multiple of 16 doubles (128 B rows).  The reference's AoS layout
+ * A[Emax*id+n], id = Xmax*Ymax*k + Xmax*j + i (src/solver_UpdateStates/Update_kernels.hpp:14-15, also the
+ * payload of its checkpoint file, src/XFLUIDS.cpp:658-687) is what xf_upload_aos/xf_download_aos speak.
+ *
+ * There is no CPU fallback: every function fails with XF_ERR_CUDA when no device is usable.
+ */
+#ifndef XFLUIDS_B200_H
+#define XFLUIDS_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum xf_status {
+	XF_OK = 0,
+	XF_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+	XF_ERR_CUDA = -2,     /* CUDA runtime error (xf_last_error() has the text) */
+	XF_ERR_NUMERIC = -3,  /* a guard kernel found NaN/Inf/negative state (reference "error captured") */
+	XF_ERR_COMM = -4      /* multi-GPU exchange error */
+} xf_status;
+
+/* reference enum BConditions, src/include/global_setup.h:96-110 */
+enum { XF_BC_INFLOW = 0, XF_BC_OUTFLOW = 1, XF_BC_SYMMETRY = 2, XF_BC_PERIODIC = 3, XF_BC_NSLIPWALL = 4,
+       XF_BC_VISCWALL = 5, XF_BC_SLIPWALL = 6, XF_BC_INNERBLOCK = 7, XF_BC_COPY = 99 /* neighbour rank: halo */ };
+
+/* the fields of reference struct Block / MeshSize (global_setup.h:155-190) that the path uses;
+ * metric formulas are the caller's (reference src/read_ini/src/iniset.cpp:290-336). */
+typedef struct xf_block {
+	int X_inner, Y_inner, Z_inner;
+	int Bwidth_X, Bwidth_Y, Bwidth_Z;   /* 0 in an inactive dimension */
+	int Xmax, Ymax, Zmax;               /* inner + 2*Bwidth, 1 in an inactive dimension */
+	int DimX, DimY, DimZ;
+	double dx, dy, dz, _dx, _dy, _dz;   /* _dx = 1/dx exactly as the host computed it */
+	double CFLnumber;
+} xf_block;
+
+/* reference struct Thermal (global_setup.h:192-199) + the compile-time mixture macros made run-time */
+typedef struct xf_thermal {
+	int num_species;       /* NUM_SPECIES (1 when cop == 0) */
+	int cop;               /* 1: multi-component (COP), NASA-9 thermo; 0: single gamma-law gas */
+	int ghost_species;     /* GhostSpecies: last species is inert filler, Y renormalised (Update_device.hpp:15-22) */
+	double ncop_gamma;     /* NCOP_Gamma (cop == 0) */
+	const double *Hia;     /* host, [num_species*7*3]  Hia[n*21 + m*3 + range]   (src/read_ini/src/thermal.cpp:50-88) */
+	const double *Hib;     /* host, [num_species*2*3] */
+	const double *Ri;      /* host, [num_species]  Ru/Wi */
+	const double *_Wi;     /* host, [num_species]  1/Wi  */
+} xf_thermal;
+
+/* reference compile-time scheme macros (cmake/init_options.cmake) made run-time */
+typedef struct xf_scheme {
+	int weno_order;        /* SCHEME_ORDER: 5 (WENO5-JS, weno5old) or 7 (WENO7-JS) */
+	int artificial_type;   /* Artificial_type: 1 ROE, 2 LLF, 3 GLF */
+	int fp_mode;           /* 0 strict: no FMA contraction, reference summation order (parity mode);
+	                          1 fast:   FMA contraction allowed (same formulas, same order) */
+} xf_scheme;
+
+typedef struct xf_ctx xf_ctx;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* replaces Fluid::AllocateFluidMemory + Setup::CpyToGPU (Fluids.cpp:270-583, src/read_ini/src/gpucopy.cpp:5-36):
+ * allocates the primitive / wall-flux work arrays and uploads the thermo tables. */
+int xf_create(const xf_block *bl, const xf_thermal *th, const xf_scheme *sc, int device, xf_ctx **out);
+int xf_destroy(xf_ctx *ctx);
+const char *xf_last_error(void);
+int xf_set_stream(xf_ctx *ctx, void *cuda_stream);   /* all later launches go to this stream (default: 0) */
+int xf_synchronize(xf_ctx *ctx);
+
+/* ---- geometry of the device layout ------------------------------------------------------------ */
+size_t xf_pitch(const xf_ctx *ctx);          /* padded x extent, in doubles */
+size_t xf_field_stride(const xf_ctx *ctx);   /* doubles between consecutive components n of one field */
+size_t xf_field_doubles(const xf_ctx *ctx);  /* Emax * field_stride: size of U, U1 or LU */
+int xf_emax(const xf_ctx *ctx);
+
+/* ---- conserved-variable fields owned by the caller (reference Fluid::d_U, d_U1, d_LU) ----------- */
+int xf_field_alloc(xf_ctx *ctx, double **d_field);           /* zero-filled */
+int xf_field_free(xf_ctx *ctx, double *d_field);
+int xf_upload_aos(xf_ctx *ctx, double *d_field, const double *h_aos);        /* host AoS [N*Emax] -> device SoA */
+int xf_download_aos(xf_ctx *ctx, const double *d_field, double *h_aos);      /* device SoA -> host AoS */
+/* scalar work arrays by reference name: "T" "p" "u" "v" "w" "H" "c" "rho" "gamma" "e" ; y as "y<k>".
+ * set: host [N] in reference cell order -> device; get: device -> host.  T must be set before the first
+ * xf_update_states: it is the Newton warm start and a state variable. */
+int xf_set_scalar(xf_ctx *ctx, const char *name, const double *h);
+int xf_get_scalar(xf_ctx *ctx, const char *name, double *h);
+int xf_get_wallflux_aos(xf_ctx *ctx, int dir, double *h_aos);                /* FluxFw/Gw/Hw of the last xf_get_lu */
+
+/* ---- the block-level entry points (all asynchronous on the ctx stream unless they return a host value) */
+/* float FluidBoundaryCondition(queue&, Setup, BConditions[6], real_t*)   src/solver_BCs/BCs_block.cpp:4-218 */
+int xf_boundary(xf_ctx *ctx, double *d_UI, const int bc[6]);
+/* pair<bool,...> UpdateFluidStateFlux(queue&, Setup, Thermal, real_t *UI, FlowData&, ...)
+ *                                     src/solver_UpdateStates/UpdateStates_block.cpp:7-191 (K1..K4; mutates UI under GhostSpecies).
+ * error (may be NULL): receives 1 when a guard fired (synchronises); NULL keeps the call asynchronous. */
+int xf_update_states(xf_ctx *ctx, double *d_UI, int *error);
+/* vector<float> GetLU(queue&, Setup&, Block, BConditions[6], Thermal, real_t *UI, real_t *LU, ...)
+ *                                     src/solver_Reconstruction/FDM_Method/ConVenction_block.hpp:10-617 (inviscid branch) */
+int xf_get_lu(xf_ctx *ctx, const double *d_UI, double *d_LU);
+/* bool Fluid::EstimateFluidNAN(queue&, int flag)   src/Fluids.cpp:963-1040 */
+int xf_estimate_nan(xf_ctx *ctx, const double *d_UI, const double *d_LU, int *error);
+/* void UpdateURK3rd(queue&, Block, real_t *U, real_t *U1, real_t *LU, real_t dt, int flag)
+ *                                     src/solver_UpdateStates/UpdateStates_block.cpp:193-211 */
+int xf_update_u_rk3(xf_ctx *ctx, double *d_U, double *d_U1, const double *d_LU, double dt, int flag);
+/* real_t GetDt(queue&, Block, Thermal&, FlowData&, real_t *uvw_c_max)   src/solver_GetDt/GlobalDt_block.hpp:6-114
+ * uvw_c_max (may be NULL) receives the three directional maxima (for the cross-rank MAX reduction). */
+int xf_get_dt(xf_ctx *ctx, double *dt, double uvw_c_max[3]);
+
+/* ---- fused path: one SSP-RK3 stage / whole steps, state stays on the device ----------------------- */
+/* XFLUIDS::RungeKuttaSP3rd (src/XFLUIDS.cpp:441-525): BC -> UpdateStates -> GetLU -> NaN guard -> UpdateU.
+ * dt is read from the device-resident value written by xf_dt_device. */
+int xf_rk_stage(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const int bc[6], int flag);
+/* device-resident ComputeTimeStep (src/XFLUIDS.cpp:196-199,527-544): dt = CFL / sum(max_d * _dd), clipped so that
+ * time + dt <= t_end; time += dt.  Uses the maxima gathered by the last xf_update_states. */
+int xf_dt_device(xf_ctx *ctx, double t_end);
+/* nsteps time steps of XFLUIDS::Evolution's inner loop (src/XFLUIDS.cpp:172-294) without host round trips
+ * (captured once into a CUDA graph and replayed).  Stops early at t_end.  Synchronises at the end. */
+int xf_run(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const int bc[6], int nsteps, double t_end,
+           int *steps_done, double *time_out, int *error);
+int xf_get_time(xf_ctx *ctx, double *time, double *last_dt);
+int xf_set_time(xf_ctx *ctx, double time);
+int xf_error_flags(xf_ctx *ctx, int flags[4]);      /* [0] rho/Yi guard [1] primitive guard [2] U/LU NaN guard; synchronises */
+int xf_clear_errors(xf_ctx *ctx);
+/* device addresses for the multi-GPU glue (one process per GPU; the exchange itself is the caller's NCCL/P2P):
+ * the 3 directional dt maxima (double[3]) and the error word (int[4]). */
+double *xf_device_dtmax(xf_ctx *ctx);
+int *xf_device_errors(xf_ctx *ctx);
+
+/* ---- z-slab halo (replaces FluidMpiCopyKernelZ pack/unpack, src/solver_BCs/BCs_kernels.hpp:304-324 and
+ *      MpiTrans::MpiTransBuf, src/mpiPacks/mpiPacks.cpp:357-505): Bwidth_Z planes x Emax, contiguous per component */
+size_t xf_halo_doubles(const xf_ctx *ctx);                               /* Emax * Bwidth_Z * Ymax * pitch */
+int xf_halo_pack(xf_ctx *ctx, const double *d_UI, int face, double *d_buf);   /* face 4 = zmin inner planes, 5 = zmax */
+int xf_halo_unpack(xf_ctx *ctx, double *d_UI, int face, const double *d_buf); /* into the ghost planes of that face */
+
+/* ---- host-buffer convenience used for end-to-end timing: upload AoS U, run nsteps, download AoS U ---- */
+int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nsteps, double t_end,
+                 double *d_U, double *d_U1, double *d_LU, int *steps_done, int *error);
+void *xf_host_alloc_pinned(size_t bytes);
+void xf_host_free_pinned(void *p);
+
+/* kernel launch counter (bench.py "gpu_launches") */
+long long xf_launch_count(const xf_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,564 @@
+// xf_capi.cu -- the C-ABI layer of libxfluids_b200.so (include/xfluids_b200.h): context, memory, dispatch to the
+// strict / fast kernel flavours, CUDA-graph replay of whole time steps.  No CPU fallback anywhere: every entry
+// point ends in a kernel launch or a CUDA memory operation on the context's device and stream.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/xfluids_b200.h"
+#include "xf_launch.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &m)
+{
+	g_err = m;
+	return code;
+}
+#define CU(call)                                                                                        \
+	do                                                                                                  \
+	{                                                                                                   \
+		cudaError_t e__ = (call);                                                                       \
+		if (e__ != cudaSuccess)                                                                         \
+			return fail(XF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+	} while (0)
+#define KL(call)                                                                                        \
+	do                                                                                                  \
+	{                                                                                                   \
+		int r__ = (call);                                                                               \
+		if (r__ > 0)                                                                                    \
+			return fail(XF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString((cudaError_t)r__)); \
+		if (r__ < 0)                                                                                    \
+			return fail(XF_ERR_ARG, std::string(#call) + ": unsupported configuration");                \
+	} while (0)
+
+struct XfTable
+{
+	decltype(&xf_strict::launch_prim) prim;
+	decltype(&xf_strict::launch_sweeps) sweeps;
+	decltype(&xf_strict::launch_lu) lu;
+	decltype(&xf_strict::launch_rk) rk;
+	decltype(&xf_strict::launch_nan) nan;
+	decltype(&xf_strict::launch_bc) bc;
+	decltype(&xf_strict::launch_dt) dt;
+	decltype(&xf_strict::launch_dt_final) dt_final;
+	decltype(&xf_strict::launch_layout) layout;
+	decltype(&xf_strict::launch_scalar_pad) scalar_pad;
+	decltype(&xf_strict::launch_halo) halo;
+};
+static const XfTable T_STRICT = {xf_strict::launch_prim, xf_strict::launch_sweeps, xf_strict::launch_lu, xf_strict::launch_rk, xf_strict::launch_nan,
+								 xf_strict::launch_bc, xf_strict::launch_dt, xf_strict::launch_dt_final, xf_strict::launch_layout,
+								 xf_strict::launch_scalar_pad, xf_strict::launch_halo};
+static const XfTable T_FAST = {xf_fast::launch_prim, xf_fast::launch_sweeps, xf_fast::launch_lu, xf_fast::launch_rk, xf_fast::launch_nan,
+							   xf_fast::launch_bc, xf_fast::launch_dt, xf_fast::launch_dt_final, xf_fast::launch_layout,
+							   xf_fast::launch_scalar_pad, xf_fast::launch_halo};
+
+struct xf_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	xf_block bl{};
+	xf_scheme sc{};
+	int ns = 1, cop = 0, ghost = 0, E = 5;
+	XfDev d{};
+	XfThermo th{};
+	const XfTable *t = nullptr;
+	std::vector<void *> owned;      // device allocations freed in xf_destroy
+	double *stage = nullptr;        // device staging for AoS import/export [Ncells*E]
+	double *h_pin = nullptr;        // pinned host scratch (16 doubles)
+	int *h_err = nullptr;           // pinned host error word (4 ints)
+	long long launches = 0;
+	const double *lastUI = nullptr; // field of the last xf_update_states (its component 0 is rho)
+	// CUDA graph of one time step (xf_run)
+	cudaGraphExec_t gexec = nullptr;
+	const double *gU = nullptr, *gU1 = nullptr, *gLU = nullptr;
+	int gbc[6] = {-1, -1, -1, -1, -1, -1};
+	double gt_end = 0;
+	long long glaunches = 0; // kernel launches inside one replay
+	size_t ncells() const { return size_t(bl.Xmax) * bl.Ymax * bl.Zmax; }
+};
+
+static int dmalloc(xf_ctx *c, double **p, size_t n)
+{
+	CU(cudaMalloc((void **)p, n * sizeof(double)));
+	CU(cudaMemsetAsync(*p, 0, n * sizeof(double), c->stream));
+	c->owned.push_back(*p);
+	return 0;
+}
+
+extern "C"
+{
+	const char *xf_last_error(void) { return g_err.c_str(); }
+
+	int xf_create(const xf_block *bl, const xf_thermal *th, const xf_scheme *sc, int device, xf_ctx **out)
+	{
+		if (!bl || !th || !sc || !out)
+			return fail(XF_ERR_ARG, "null argument");
+		int ndev = 0;
+		if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+			return fail(XF_ERR_CUDA, "no usable CUDA device (this library has no CPU path)");
+		CU(cudaSetDevice(device));
+		if (sc->weno_order != 5 && sc->weno_order != 7)
+			return fail(XF_ERR_ARG, "weno_order must be 5 or 7");
+		if (sc->artificial_type < 1 || sc->artificial_type > 3)
+			return fail(XF_ERR_ARG, "artificial_type must be 1 (ROE), 2 (LLF) or 3 (GLF)");
+		if (th->cop && (th->num_species < 2 || th->num_species > 5))
+			return fail(XF_ERR_ARG, "multi-component path is instantiated for 2..5 species");
+		if (bl->Xmax < 1 || bl->Ymax < 1 || bl->Zmax < 1)
+			return fail(XF_ERR_ARG, "bad block");
+		const int minw = sc->weno_order == 7 ? 4 : 3;
+		if ((bl->DimX && bl->Bwidth_X < minw) || (bl->DimY && bl->Bwidth_Y < minw) || (bl->DimZ && bl->Bwidth_Z < minw))
+			return fail(XF_ERR_ARG, "ghost width too small for the stencil");
+		xf_ctx *c = new xf_ctx();
+		c->device = device;
+		c->bl = *bl, c->sc = *sc;
+		c->cop = th->cop ? 1 : 0, c->ns = th->cop ? th->num_species : 1, c->ghost = th->ghost_species ? 1 : 0;
+		c->E = c->cop ? c->ns + 4 : 5;
+		c->t = sc->fp_mode ? &T_FAST : &T_STRICT;
+		XfDev &d = c->d;
+		d.Xmax = bl->Xmax, d.Ymax = bl->Ymax, d.Zmax = bl->Zmax;
+		d.Xp = (bl->Xmax + XF_PITCH_ALIGN - 1) / XF_PITCH_ALIGN * XF_PITCH_ALIGN;
+		d.Xi = bl->X_inner, d.Yi = bl->Y_inner, d.Zi = bl->Z_inner;
+		d.Bx = bl->Bwidth_X, d.By = bl->Bwidth_Y, d.Bz = bl->Bwidth_Z;
+		d.DimX = bl->DimX, d.DimY = bl->DimY, d.DimZ = bl->DimZ;
+		d.weno = sc->weno_order, d.alpha = sc->artificial_type, d.ghost = c->ghost;
+		d.sY = d.Xp, d.sZ = (long long)d.Xp * d.Ymax, d.N = d.sZ * d.Zmax;
+		d._dx = bl->_dx, d._dy = bl->_dy, d._dz = bl->_dz, d.CFL = bl->CFLnumber, d.gamma0 = th->ncop_gamma;
+		// thermo tables (Thermo_device.h coefficient use; products formed exactly as the reference forms them)
+		std::memset(&c->th, 0, sizeof(XfThermo));
+		c->th.Ru = (6.02214076e26 * 1.380649e-23) * 1.0E-3; // global_setup.h:49-54
+		if (c->cop)
+		{
+			const double _OT = 1.0 / 3.0;
+			for (int n = 0; n < c->ns; n++)
+			{
+				for (int r = 0; r < 3; r++)
+				{
+					const double *a = th->Hia + n * 21;
+					double *h = c->th.hcoef[r][n], *cc = c->th.ccoef[r][n];
+					h[0] = -a[0 * 3 + r], h[1] = a[1 * 3 + r], h[2] = a[2 * 3 + r], h[3] = 0.5 * a[3 * 3 + r];
+					h[4] = a[4 * 3 + r] * _OT, h[5] = 0.25 * a[5 * 3 + r], h[6] = 0.2 * a[6 * 3 + r], h[7] = th->Hib[n * 6 + 0 * 3 + r];
+					for (int m = 0; m < 7; m++)
+						cc[m] = a[m * 3 + r];
+				}
+				c->th.Ri[n] = th->Ri[n], c->th._Wi[n] = th->_Wi[n];
+			}
+		}
+		const size_t N = (size_t)d.N;
+		int rc = 0;
+		double **sc_arr[] = {&d.u, &d.v, &d.w, &d.p, &d.H, &d.c, &d.T};
+		for (double **p : sc_arr)
+			rc |= dmalloc(c, p, N);
+		if (c->cop)
+		{
+			double **cop_arr[] = {&d.g3, &d.dpdrho, &d.e, &d.prho};
+			for (double **p : cop_arr)
+				rc |= dmalloc(c, p, N);
+			rc |= dmalloc(c, &d.y, N * c->ns);
+			rc |= dmalloc(c, &d.dpdrhoi, N * (c->ns - 1));
+		}
+		for (int dir = 0; dir < 3; dir++)
+			if ((dir == 0 && d.DimX) || (dir == 1 && d.DimY) || (dir == 2 && d.DimZ))
+				rc |= dmalloc(c, &d.Fw[dir], N * c->E);
+		rc |= dmalloc(c, &d.red, XF_RED_COUNT);
+		double *errp = nullptr;
+		rc |= dmalloc(c, &errp, 2);
+		d.err = reinterpret_cast<int *>(errp);
+		if (rc)
+		{
+			xf_destroy(c);
+			return rc;
+		}
+		CU(cudaMallocHost((void **)&c->h_pin, 16 * sizeof(double)));
+		CU(cudaMallocHost((void **)&c->h_err, 4 * sizeof(int)));
+		CU(cudaStreamSynchronize(c->stream));
+		*out = c;
+		return XF_OK;
+	}
+
+	int xf_destroy(xf_ctx *c)
+	{
+		if (!c)
+			return XF_OK;
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+		if (c->gexec)
+			cudaGraphExecDestroy(c->gexec);
+		for (void *p : c->owned)
+			cudaFree(p);
+		if (c->stage)
+			cudaFree(c->stage);
+		if (c->h_pin)
+			cudaFreeHost(c->h_pin);
+		if (c->h_err)
+			cudaFreeHost(c->h_err);
+		delete c;
+		return XF_OK;
+	}
+	int xf_set_stream(xf_ctx *c, void *s)
+	{
+		c->stream = (cudaStream_t)s;
+		if (c->gexec)
+			cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+		return XF_OK;
+	}
+	int xf_synchronize(xf_ctx *c)
+	{
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+	size_t xf_pitch(const xf_ctx *c) { return (size_t)c->d.Xp; }
+	size_t xf_field_stride(const xf_ctx *c) { return (size_t)c->d.N; }
+	size_t xf_field_doubles(const xf_ctx *c) { return (size_t)c->d.N * c->E; }
+	int xf_emax(const xf_ctx *c) { return c->E; }
+	long long xf_launch_count(const xf_ctx *c) { return c->launches; }
+	double *xf_device_dtmax(xf_ctx *c) { return c->d.red + XF_RED_DTMAX; }
+	int *xf_device_errors(xf_ctx *c) { return c->d.err; }
+
+	int xf_field_alloc(xf_ctx *c, double **p)
+	{
+		CU(cudaSetDevice(c->device));
+		CU(cudaMalloc((void **)p, xf_field_doubles(c) * sizeof(double)));
+		CU(cudaMemsetAsync(*p, 0, xf_field_doubles(c) * sizeof(double), c->stream));
+		return XF_OK;
+	}
+	int xf_field_free(xf_ctx *c, double *p)
+	{
+		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaFree(p));
+		return XF_OK;
+	}
+	static int ensure_stage(xf_ctx *c)
+	{
+		if (!c->stage)
+			CU(cudaMalloc((void **)&c->stage, c->ncells() * c->E * sizeof(double)));
+		return 0;
+	}
+	int xf_upload_aos(xf_ctx *c, double *d_field, const double *h_aos)
+	{
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		CU(cudaMemcpyAsync(c->stage, h_aos, c->ncells() * c->E * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		KL(c->t->layout(c->d, c->E, d_field, c->stage, 1, c->stream));
+		c->launches++;
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+	int xf_download_aos(xf_ctx *c, const double *d_field, double *h_aos)
+	{
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		KL(c->t->layout(c->d, c->E, const_cast<double *>(d_field), c->stage, 0, c->stream));
+		c->launches++;
+		CU(cudaMemcpyAsync(h_aos, c->stage, c->ncells() * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+	static double *scalar_by_name(xf_ctx *c, const char *name)
+	{
+		XfDev &d = c->d;
+		if (!std::strcmp(name, "T")) return d.T;
+		if (!std::strcmp(name, "p")) return d.p;
+		if (!std::strcmp(name, "u")) return d.u;
+		if (!std::strcmp(name, "v")) return d.v;
+		if (!std::strcmp(name, "w")) return d.w;
+		if (!std::strcmp(name, "H")) return d.H;
+		if (!std::strcmp(name, "c")) return d.c;
+		if (c->cop && name[0] == 'y' && name[1] >= '0' && name[1] < '0' + c->ns && !name[2])
+			return d.y + (size_t)(name[1] - '0') * d.N;
+		return nullptr;
+	}
+	int xf_set_scalar(xf_ctx *c, const char *name, const double *h)
+	{
+		double *p = scalar_by_name(c, name);
+		if (!p)
+			return fail(XF_ERR_ARG, std::string("unknown scalar ") + name);
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		CU(cudaMemcpyAsync(c->stage, h, c->ncells() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		KL(c->t->scalar_pad(c->d, p, c->stage, 1, c->stream));
+		c->launches++;
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+	int xf_get_scalar(xf_ctx *c, const char *name, double *h)
+	{
+		double *p = scalar_by_name(c, name);
+		if (!p)
+			return fail(XF_ERR_ARG, std::string("unknown scalar ") + name);
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		KL(c->t->scalar_pad(c->d, p, c->stage, 0, c->stream));
+		c->launches++;
+		CU(cudaMemcpyAsync(h, c->stage, c->ncells() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+	int xf_get_wallflux_aos(xf_ctx *c, int dir, double *h_aos)
+	{
+		if (dir < 0 || dir > 2 || !c->d.Fw[dir])
+			return fail(XF_ERR_ARG, "inactive direction");
+		return xf_download_aos(c, c->d.Fw[dir], h_aos);
+	}
+
+	// ---- block-level entry points ---------------------------------------------------------------
+	int xf_boundary(xf_ctx *c, double *U, const int bc[6])
+	{
+		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches));
+		return XF_OK;
+	}
+	static int update_states(xf_ctx *c, double *U, bool gather_dt)
+	{
+		int flags = 0;
+		if (gather_dt)
+		{
+			CU(cudaMemsetAsync(c->d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
+			flags |= 1;
+		}
+		if (c->sc.artificial_type == 3 && c->sc.weno_order != 7)
+			flags |= 2; // GLF running maxima; for SCHEME_ORDER 7 eigen_local == 0 and the maxima stay 0
+		KL(c->t->prim(c->d, c->th, c->ns, c->cop, U, flags, c->stream));
+		c->launches++;
+		c->lastUI = U;
+		return XF_OK;
+	}
+	int xf_error_flags(xf_ctx *c, int flags[4])
+	{
+		CU(cudaMemcpyAsync(c->h_err, c->d.err, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < 4; i++)
+			flags[i] = c->h_err[i];
+		return XF_OK;
+	}
+	int xf_clear_errors(xf_ctx *c)
+	{
+		CU(cudaMemsetAsync(c->d.err, 0, 4 * sizeof(int), c->stream));
+		return XF_OK;
+	}
+	int xf_update_states(xf_ctx *c, double *U, int *error)
+	{
+		int rc = update_states(c, U, true);
+		if (rc)
+			return rc;
+		if (error)
+		{
+			int f[4];
+			if ((rc = xf_error_flags(c, f)))
+				return rc;
+			*error = (f[0] || f[1]) ? 1 : 0;
+		}
+		return XF_OK;
+	}
+	int xf_get_lu(xf_ctx *c, const double *U, double *LU)
+	{
+		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches));
+		KL(c->t->lu(c->d, c->E, LU, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	int xf_estimate_nan(xf_ctx *c, const double *UI, const double *LU, int *error)
+	{
+		KL(c->t->nan(c->d, c->E, UI, LU, c->stream));
+		c->launches++;
+		if (error)
+		{
+			int f[4], rc;
+			if ((rc = xf_error_flags(c, f)))
+				return rc;
+			*error = f[2] ? 1 : 0;
+		}
+		return XF_OK;
+	}
+	int xf_update_u_rk3(xf_ctx *c, double *U, double *U1, const double *LU, double dt, int flag)
+	{
+		if (flag < 1 || flag > 3)
+			return fail(XF_ERR_ARG, "flag must be 1..3");
+		KL(c->t->rk(c->d, c->E, U, U1, LU, dt, nullptr, flag, 0, 0, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	int xf_get_dt(xf_ctx *c, double *dt, double uvw_c_max[3])
+	{
+		// stand-alone reduction pass over the stored primitives, like the reference's GetDt; rho is component 0 of
+		// the field the primitives were last derived from (the reference keeps a separate rho array)
+		if (!c->lastUI)
+			return fail(XF_ERR_ARG, "xf_get_dt before any xf_update_states");
+		CU(cudaMemsetAsync(c->d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
+		KL(c->t->dt(c->d, c->lastUI, c->stream));
+		c->launches++;
+		CU(cudaMemcpyAsync(c->h_pin, c->d.red + XF_RED_DTMAX, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		const double *m = c->h_pin;
+		if (uvw_c_max)
+			uvw_c_max[0] = m[0], uvw_c_max[1] = m[1], uvw_c_max[2] = m[2];
+		const double dtref = m[0] * c->bl._dx + m[1] * c->bl._dy + m[2] * c->bl._dz;
+		*dt = c->bl.CFLnumber / dtref;
+		return XF_OK;
+	}
+
+	// ---- fused path --------------------------------------------------------------------------------
+	int xf_dt_device(xf_ctx *c, double t_end)
+	{
+		KL(c->t->dt_final(c->d, t_end, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	int xf_rk_stage(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int flag)
+	{
+		if (flag < 1 || flag > 3)
+			return fail(XF_ERR_ARG, "flag must be 1..3");
+		double *UI = flag == 1 ? U : U1;
+		int rc;
+		if (bc && (rc = xf_boundary(c, UI, bc)))
+			return rc;
+		// the dt of the NEXT step is computed from the primitives of stage 3 (XFLUIDS.cpp:196 reads fdata as left
+		// by the last UpdateStates) -> gather the maxima there
+		if ((rc = update_states(c, UI, flag == 3)))
+			return rc;
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches));
+		// flux divergence + NaN guard + RK update in one kernel; LU stays in registers
+		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	int xf_get_time(xf_ctx *c, double *time, double *last_dt)
+	{
+		CU(cudaMemcpyAsync(c->h_pin, c->d.red + XF_RED_DT, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		if (last_dt)
+			*last_dt = c->h_pin[0];
+		if (time)
+			*time = c->h_pin[1];
+		return XF_OK;
+	}
+	int xf_set_time(xf_ctx *c, double time)
+	{
+		c->h_pin[8] = time;
+		CU(cudaMemcpyAsync(c->d.red + XF_RED_TIME, c->h_pin + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		return XF_OK;
+	}
+
+	static int enqueue_step(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], double t_end)
+	{
+		int rc;
+		if ((rc = xf_dt_device(c, t_end)))
+			return rc;
+		for (int flag = 1; flag <= 3; flag++)
+			if ((rc = xf_rk_stage(c, U, U1, LU, bc, flag)))
+				return rc;
+		return XF_OK;
+	}
+	int xf_run(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int nsteps, double t_end, int *steps_done, double *time_out, int *error)
+	{
+		CU(cudaSetDevice(c->device));
+		// (re)capture one step when pointers / BCs / t_end change
+		const bool same = c->gexec && c->gU == U && c->gU1 == U1 && c->gLU == LU && c->gt_end == t_end && !std::memcmp(c->gbc, bc, 6 * sizeof(int));
+		if (!same)
+		{
+			if (c->gexec)
+				cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+			cudaStream_t cap = c->stream;
+			cudaStream_t own = nullptr;
+			if (cap == nullptr)
+			{ // the legacy default stream cannot be captured
+				CU(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+				CU(cudaStreamSynchronize(nullptr));
+				c->stream = own;
+			}
+			const long long l0 = c->launches;
+			CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+			int rc = enqueue_step(c, U, U1, LU, bc, t_end);
+			cudaGraph_t g = nullptr;
+			cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+			c->glaunches = c->launches - l0;
+			c->launches = l0;
+			if (own)
+				c->stream = cap;
+			if (rc || e != cudaSuccess)
+			{
+				if (own)
+					cudaStreamDestroy(own);
+				return rc ? rc : fail(XF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+			}
+			CU(cudaGraphInstantiate(&c->gexec, g, 0));
+			CU(cudaGraphDestroy(g));
+			if (own)
+				CU(cudaStreamDestroy(own));
+			c->gU = U, c->gU1 = U1, c->gLU = LU, c->gt_end = t_end;
+			std::memcpy(c->gbc, bc, 6 * sizeof(int));
+		}
+		double t = 0, dt = 0;
+		int rc, done = 0, err = 0;
+		if ((rc = xf_get_time(c, &t, nullptr)))
+			return rc;
+		int poll = 1; // steps between host checks of (time, error)
+		while (done < nsteps && t < t_end)
+		{
+			int batch = poll < nsteps - done ? poll : nsteps - done;
+			for (int s = 0; s < batch; s++)
+				CU(cudaGraphLaunch(c->gexec, c->stream));
+			c->launches += c->glaunches * batch;
+			done += batch;
+			int f[4];
+			if ((rc = xf_get_time(c, &t, &dt)) || (rc = xf_error_flags(c, f)))
+				return rc;
+			if (f[0] || f[1] || f[2])
+			{
+				err = 1;
+				break;
+			}
+			// far from t_end: check less often (dt varies slowly); near it: every step, like the reference's loop
+			poll = (dt > 0 && (t_end - t) > 64.0 * dt) ? 16 : 1;
+		}
+		if (steps_done)
+			*steps_done = done;
+		if (time_out)
+			*time_out = t;
+		if (error)
+			*error = err;
+		return err ? XF_ERR_NUMERIC : XF_OK;
+	}
+
+	// ---- halo -----------------------------------------------------------------------------------
+	size_t xf_halo_doubles(const xf_ctx *c) { return (size_t)c->E * c->d.Bz * (size_t)c->d.sZ; }
+	int xf_halo_pack(xf_ctx *c, const double *U, int face, double *buf)
+	{
+		if (!c->d.DimZ || (face != 4 && face != 5))
+			return fail(XF_ERR_ARG, "halo faces are 4 (zmin) / 5 (zmax) of an active z dimension");
+		const int k0 = face == 4 ? c->d.Bz : c->d.Zmax - 2 * c->d.Bz;
+		KL(c->t->halo(c->d, c->E, const_cast<double *>(U), buf, k0, 1, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	int xf_halo_unpack(xf_ctx *c, double *U, int face, const double *buf)
+	{
+		if (!c->d.DimZ || (face != 4 && face != 5))
+			return fail(XF_ERR_ARG, "halo faces are 4 (zmin) / 5 (zmax) of an active z dimension");
+		const int k0 = face == 4 ? 0 : c->d.Zmax - c->d.Bz;
+		KL(c->t->halo(c->d, c->E, U, const_cast<double *>(buf), k0, 0, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+
+	// ---- host-buffer step (end-to-end timing path) ----------------------------------------------------
+	void *xf_host_alloc_pinned(size_t bytes)
+	{
+		void *p = nullptr;
+		return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+	}
+	void xf_host_free_pinned(void *p) { cudaFreeHost(p); }
+	int xf_step_host(xf_ctx *c, double *h_U, const int bc[6], int nsteps, double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
+	{
+		int rc;
+		if ((rc = xf_upload_aos(c, U, h_U)))
+			return rc;
+		CU(cudaMemcpyAsync(U1, U, xf_field_doubles(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		rc = xf_run(c, U, U1, LU, bc, nsteps, t_end, steps_done, nullptr, error);
+		if (rc && rc != XF_ERR_NUMERIC)
+			return rc;
+		int rc2 = xf_download_aos(c, U, h_U);
+		return rc2 ? rc2 : rc;
+	}
+}

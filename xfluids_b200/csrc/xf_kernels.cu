@@ -1,0 +1,797 @@
+// xf_kernels.cu -- hand-written sm_100a kernels of the inviscid RHS path.  Compiled twice:
+//   -DXF_NS=xf_strict -fmad=false   (parity mode: no FMA contraction)
+//   -DXF_NS=xf_fast   -fmad=true    (same formulas, contraction allowed)
+// Kernels (one launch each unless noted):
+//   k_prim      cons->prim + Newton T + per-cell pressure derivatives (+ dt / GLF maxima, guards)   a3,a4,a5,a1,a6',a10
+//   k_sweep     characteristic WENO flux at the faces of one direction, stencil staged in shared memory  a6,a7
+//   k_lu        flux divergence                                                                        a8
+//   k_rk        SSP-RK3 stage update (+ U/LU NaN guard)                                                a9,a10
+//   k_lu_rk     k_lu + k_rk fused (fast path: LU never touches HBM)
+//   k_bc        ghost-cell fill, one launch per direction                                             a2
+//   k_dt        stand-alone CFL maxima (API parity with GetDt)                                        a1
+//   k_dt_final  dt = CFL/sum, clip to t_end, advance device time
+//   k_aos2soa / k_soa2aos / k_halo_pack / k_halo_unpack   layout + z-slab halo
+#include <cuda_runtime.h>
+#include <cstdio>
+#include "xf_math.cuh"
+#include "xf_launch.h"
+
+#ifndef XF_NS
+#error "XF_NS must be defined"
+#endif
+
+namespace XF_NS
+{
+
+// ---------------------------------------------------------------------------------------------
+// reductions: warp shuffle -> one atomic per warp on the bit pattern (values are >= 0, so the
+// IEEE ordering equals the unsigned-integer ordering)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_atomic_max_pos(double *addr, double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0)
+		atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ bool xf_bad(double x) { return (x < 0) || isnan(x) || isinf(x); }
+
+// ---------------------------------------------------------------------------------------------
+// k_prim: Updaterhoyi + UpdateFuidStatesKernel (Update_kernels.hpp:5-48, Update_device.hpp:7-54) over ALL cells
+// incl. ghosts, guards (Estimate_kernels.hpp) on inner cells, and the per-cell halves of ReconstructSoundSpeed.
+// flags: bit0 gather dt maxima, bit1 gather GLF maxima
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags)
+{
+	const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = int(lin % d.Xp);
+	const long long row = lin / d.Xp;
+	const bool active = lin < d.N && i < d.Xmax;
+	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (active)
+	{
+		const long long id = lin;
+		const int j = int(row % d.Ymax), k = int(row / d.Ymax);
+		const bool inner = i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
+		constexpr int NS = C::NS, NC = C::NC;
+		const double rho = U[id];
+		const double rho1 = 1.0 / rho;
+		double yi[NS];
+		if constexpr (C::COP)
+		{
+			if (d.ghost)
+			{ // GhostSpecies: renormalise and write back into U (Update_device.hpp:15-22)
+				yi[NC] = 0.0;
+				double sum_yi = 0.0;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] = U[(5 + ii) * d.N + id] * rho1, sum_yi += yi[ii];
+				sum_yi = 1.0 / sum_yi;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] *= sum_yi, U[(5 + ii) * d.N + id] = rho * yi[ii];
+			}
+			else
+			{
+				yi[NC] = 1.0;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] = U[(5 + ii) * d.N + id] * rho1, yi[NC] += -yi[ii];
+			}
+		}
+		const double U1 = U[1 * d.N + id], U2 = U[2 * d.N + id], U3 = U[3 * d.N + id], U4 = U[4 * d.N + id];
+		const double u = U1 * rho1, v = U2 * rho1, w = U3 * rho1;
+		const double q2 = u * u + v * v + w * w;
+		const double tme = U4 * rho1 - 0.5 * q2;
+		double p, gamma, T = 0.0;
+		if constexpr (C::COP)
+		{
+			double Wm = 0.0; // sum yi/Wi
+#pragma unroll
+			for (int n = 0; n < NS; n++)
+				Wm += yi[n] * th._Wi[n];
+			const double R = Wm * th.Ru;
+			T = xf_get_T<C>(th, yi, tme, d.T[id], R);
+			p = rho * R * T;
+			const double Cp = xf_mix_cp<C>(th, yi, T);
+			// 4-argument get_CopGamma (Mixing_device.h:114-126)
+			const double CopW = 1.0 / Wm;
+			const double g4 = Cp / (Cp - th.Ru / CopW);
+			gamma = (g4 > 1.0) ? g4 : -1.0;
+			const double H = (U4 + p) * rho1;
+			// per-cell pieces of ReconstructSoundSpeed (Utils_device.hpp:102-131)
+			double hi[NS];
+			xf_species_h<C>(th, T, hi);
+			const double Cv = Cp - th.Ru * Wm;
+			const double g3 = Cp / Cv; // 3-argument get_CopGamma
+			const double prho = p / rho;
+			const double e_l = H - 0.5 * q2 - prho;
+			const double RN = th.Ri[NC];
+			const double RNT = RN * T;
+			d.dpdrho[id] = (g3 - 1.0) * (0.5 * q2 - hi[NC] + Cp * RNT / R);
+#pragma unroll
+			for (int n = 0; n < NC; n++)
+			{
+				const double hN_minus_hi = -hi[n] + hi[NC];
+				const double Ri_minus_RN = (th.Ri[n] - RN);
+				d.dpdrhoi[n * d.N + id] = (g3 - 1.0) * (hN_minus_hi + Cp * Ri_minus_RN * T / R);
+				d.y[n * d.N + id] = yi[n];
+			}
+			d.y[NC * d.N + id] = yi[NC];
+			d.g3[id] = g3, d.e[id] = e_l, d.prho[id] = prho;
+			d.T[id] = T, d.H[id] = H;
+		}
+		else
+		{
+			gamma = d.gamma0;
+			p = (d.gamma0 - 1.0) * rho * tme;
+			d.H[id] = (U4 + p) * rho1;
+		}
+		const double cc = sqrt(gamma * p * rho1);
+		d.u[id] = u, d.v[id] = v, d.w[id] = w, d.p[id] = p, d.c[id] = cc;
+
+		// guards (flag only): EstimateYiKernel / EstimatePrimitiveVarKernel, inner cells
+		if (inner)
+		{
+			bool e0 = xf_bad(rho);
+			if constexpr (C::COP)
+			{
+#pragma unroll
+				for (int n = 0; n < NS; n++)
+					e0 = e0 || isnan(yi[n]) || isinf(yi[n]);
+			}
+			if (e0)
+				d.err[0] = 1;
+			if (xf_bad(rho) || xf_bad(p) || (C::COP && xf_bad(T)))
+				d.err[1] = 1;
+		}
+		if (flags & 1)
+		{ // GetDt: hard-coded 1.4, all cells incl. ghosts (GlobalDt_block.hpp:34-66)
+			const double c_local = sqrt(1.4 * p / rho);
+			dtm[0] = fabs(u) + c_local, dtm[1] = fabs(v) + c_local, dtm[2] = fabs(w) + c_local;
+		}
+		if (flags & 2)
+		{ // GetLocalEigen maxima (Eigen_value.hpp:19-28): u_d - c, u_d, u_d + c
+			glf[0] = fabs(u - cc), glf[1] = fabs(u), glf[2] = fabs(u + cc);
+			glf[3] = fabs(v - cc), glf[4] = fabs(v), glf[5] = fabs(v + cc);
+			glf[6] = fabs(w - cc), glf[7] = fabs(w), glf[8] = fabs(w + cc);
+		}
+	}
+	if (flags & 1)
+	{
+		if (d.DimX) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 0, dtm[0]);
+		if (d.DimY) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 1, dtm[1]);
+		if (d.DimZ) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 2, dtm[2]);
+	}
+	if (flags & 2)
+	{
+#pragma unroll
+		for (int q = 0; q < 9; q++)
+			if ((q < 3 && d.DimX) || (q >= 3 && q < 6 && d.DimY) || (q >= 6 && d.DimZ))
+				warp_atomic_max_pos(d.red + XF_RED_GLF + q, glf[q]);
+	}
+}
+
+// stand-alone GetDt maxima from the stored primitives (rho is U[0])
+__global__ void __launch_bounds__(256) k_dt(XfDev d, const double *__restrict__ rho)
+{
+	const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+	if (lin < d.N && int(lin % d.Xp) < d.Xmax)
+	{
+		const double c_local = sqrt(1.4 * d.p[lin] / rho[lin]);
+		m0 = fabs(d.u[lin]) + c_local, m1 = fabs(d.v[lin]) + c_local, m2 = fabs(d.w[lin]) + c_local;
+	}
+	if (d.DimX) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 0, m0);
+	if (d.DimY) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 1, m1);
+	if (d.DimZ) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 2, m2);
+}
+
+// dt = CFL / (max_x*_dx + max_y*_dy + max_z*_dz), clipped to t_end; time += dt; maxima reset for the next gather
+__global__ void k_dt_final(XfDev d, double t_end)
+{
+	double *r = d.red;
+	const double dtref = r[XF_RED_DTMAX + 0] * d._dx + r[XF_RED_DTMAX + 1] * d._dy + r[XF_RED_DTMAX + 2] * d._dz;
+	double dt = d.CFL / dtref;
+	const double t = r[XF_RED_TIME];
+	if (t + dt > t_end)
+		dt = t_end - t;
+	r[XF_RED_DT] = dt;
+	r[XF_RED_TIME] = t + dt;
+	r[XF_RED_DTMAX + 0] = 0.0, r[XF_RED_DTMAX + 1] = 0.0, r[XF_RED_DTMAX + 2] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sweep: ReconstructFlux{X,Y,Z} (Reconstruction_kernels.hpp:8-199).  One thread per face; the stencil's conserved
+// variables, physical fluxes (GetPhysFlux, Update_device.hpp:81-110) and local wave speeds are staged once per
+// tile in shared memory as SoA pencils [component][cell], so a face reads its NST cells conflict-free.
+//   DIR 0: tile = 128 consecutive cells of the linear index space (rows are contiguous; non-face cells idle)
+//   DIR 1/2: tile = 32 (x) x TF faces along the sweep; staged rows = TF + NST - 1
+// ---------------------------------------------------------------------------------------------
+template <class C, int WENO>
+struct SmemStencil
+{
+	const double *sU, *sF, *sL; // [E][ncell], [E][ncell], [3][ncell]
+	int ncell, base, stride;    // cell index of stencil slot s: base + s*stride
+	__device__ __forceinline__ double U(int s, int n) const { return sU[n * ncell + base + s * stride]; }
+	__device__ __forceinline__ double F(int s, int n) const { return sF[n * ncell + base + s * stride]; }
+	__device__ __forceinline__ double lam(int s, int t) const { return sL[t * ncell + base + s * stride]; }
+};
+
+template <class C, int DIR>
+__device__ __forceinline__ void stage_cell(const XfDev &d, const double *__restrict__ U, long long id, bool valid,
+										   double *sU, double *sF, double *sL, int ncell, int c)
+{
+	constexpr int E = C::E, NC = C::NC;
+	if (!valid)
+	{
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			sU[n * ncell + c] = 0.0, sF[n * ncell + c] = 0.0;
+		sL[c] = 0.0, sL[ncell + c] = 0.0, sL[2 * ncell + c] = 0.0;
+		return;
+	}
+	double Uc[E];
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		Uc[n] = U[n * d.N + id];
+	const double u = d.u[id], v = d.v[id], w = d.w[id], p = d.p[id], cc = d.c[id];
+	const double un = DIR == 0 ? u : (DIR == 1 ? v : w);
+	const double m = Uc[1 + DIR]; // rho*u_d
+	double Fc[E];
+	Fc[0] = m;
+	Fc[1] = DIR == 0 ? m * u + p : m * u;
+	Fc[2] = DIR == 1 ? m * v + p : m * v;
+	Fc[3] = DIR == 2 ? m * w + p : m * w;
+	Fc[4] = (Uc[4] + p) * un;
+#pragma unroll
+	for (int s = 0; s < NC; s++)
+		Fc[5 + s] = m * d.y[s * d.N + id];
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		sU[n * ncell + c] = Uc[n], sF[n * ncell + c] = Fc[n];
+	sL[c] = fabs(un - cc), sL[ncell + c] = fabs(un), sL[2 * ncell + c] = fabs(un + cc);
+}
+
+template <class C>
+__device__ __forceinline__ void load_side(const XfDev &d, const double *__restrict__ U, long long id, XfSide<C> &s)
+{
+	s.rho = U[id], s.u = d.u[id], s.v = d.v[id], s.w = d.w[id], s.H = d.H[id], s.p = d.p[id];
+	if constexpr (C::COP)
+	{
+		s.g3 = d.g3[id], s.dpdrho = d.dpdrho[id], s.e = d.e[id], s.prho = d.prho[id];
+#pragma unroll
+		for (int n = 0; n < C::NC; n++)
+			s.y[n] = d.y[n * d.N + id], s.dpdrhoi[n] = d.dpdrhoi[n * d.N + id];
+	}
+}
+
+constexpr int XF_TX = 128; // x-sweep: faces (cells) per block
+constexpr int XF_TW = 32;  // y/z sweeps: tile width in x
+constexpr int XF_TF = 8;   // y/z sweeps: faces per tile along the sweep
+
+template <class C, int DIR, int WENO>
+__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
+{
+	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
+	extern __shared__ double smem[];
+	XfSide<C> sl, sr;
+	SmemStencil<C, WENO> st;
+	long long id_l;
+	bool valid;
+
+	if constexpr (DIR == 0)
+	{
+		constexpr int ncell = XF_TX + NST - 1;
+		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
+		// linear cell range of this block inside the inner z-planes
+		const long long id0 = (long long)d.Bz * d.sZ + (long long)blockIdx.x * XF_TX;
+		for (int c = threadIdx.x; c < ncell; c += XF_TX)
+		{
+			const long long id = id0 - P + c;
+			const bool ok = id >= 0 && id < d.N && int(id % d.Xp) < d.Xmax;
+			stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, c);
+		}
+		__syncthreads();
+		id_l = id0 + threadIdx.x;
+		const int i = int(id_l % d.Xp);
+		const long long row = id_l / d.Xp;
+		const int j = int(row % d.Ymax), k = int(row / d.Ymax);
+		valid = id_l < d.N && i >= d.Bx - 1 && i < d.Bx + d.Xi && j >= d.By && j < d.By + d.Yi && k >= d.Bz && k < d.Bz + d.Zi;
+		st.sU = sU, st.sF = sF, st.sL = sL, st.ncell = ncell, st.base = threadIdx.x, st.stride = 1;
+		if (valid)
+			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + 1, sr);
+	}
+	else
+	{
+		constexpr int nrow = XF_TF + NST - 1, ncell = nrow * XF_TW;
+		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
+		const int tx = threadIdx.x % XF_TW, ty = threadIdx.x / XF_TW;
+		const int i = d.Bx + blockIdx.x * XF_TW + tx;
+		// faces along the sweep start at B-1 ; the other transverse index is inner
+		int j, k, f0;
+		long long sS; // cell stride along the sweep
+		if constexpr (DIR == 1)
+			f0 = d.By - 1 + blockIdx.y * XF_TF, k = d.Bz + blockIdx.z, j = 0, sS = d.sY;
+		else
+			f0 = d.Bz - 1 + blockIdx.z * XF_TF, j = d.By + blockIdx.y, k = 0, sS = d.sZ;
+		const int nmax = DIR == 1 ? d.Ymax : d.Zmax;
+		const bool iok = i < d.Bx + d.Xi;
+		for (int r = ty; r < nrow; r += XF_TF)
+		{
+			const int q = f0 - P + r; // index along the sweep of this staged row
+			const bool ok = iok && q >= 0 && q < nmax;
+			const long long id = DIR == 1 ? ((long long)k * d.Ymax + q) * d.Xp + i : ((long long)q * d.Ymax + j) * d.Xp + i;
+			stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, r * XF_TW + tx);
+		}
+		__syncthreads();
+		const int qf = f0 + ty; // left cell of this thread's face
+		const int qend = DIR == 1 ? d.By + d.Yi : d.Bz + d.Zi;
+		valid = iok && qf < qend;
+		id_l = DIR == 1 ? ((long long)k * d.Ymax + qf) * d.Xp + i : ((long long)qf * d.Ymax + j) * d.Xp + i;
+		st.sU = sU, st.sF = sF, st.sL = sL, st.ncell = ncell, st.base = ty * XF_TW + tx, st.stride = XF_TW;
+		if (valid)
+			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + sS, sr);
+	}
+	if (!valid)
+		return;
+	XfRoe<C> R;
+	xf_roe_state<C>(sl, sr, d.gamma0, R);
+	double glf[3] = {d.red[XF_RED_GLF + DIR * 3 + 0], d.red[XF_RED_GLF + DIR * 3 + 1], d.red[XF_RED_GLF + DIR * 3 + 2]};
+	double F[E];
+	xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, F);
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		Fw[n * d.N + id_l] = F[n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_lu: UpdateFluidLU (Reconstruction_kernels.hpp:201-234); k_rk: UpdateURK3rdKernel (Update_kernels.hpp:64-94) with
+// EstimateFluidNANKernel (Fluids.cpp:47-87) folded in; k_lu_rk: both, LU kept in registers.
+// One thread per inner cell, x fastest.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool inner_cell(const XfDev &d, long long &id)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = int(t % d.Xi);
+	const long long r = t / d.Xi;
+	const int j = int(r % d.Yi);
+	const long long k = r / d.Yi;
+	if (k >= d.Zi)
+		return false;
+	id = ((k + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
+	return true;
+}
+__device__ __forceinline__ double lu_of(const XfDev &d, long long o)
+{
+	double LU0 = 0.0;
+	if (d.DimX)
+		LU0 += (d.Fw[0][o - 1] - d.Fw[0][o]) * d._dx;
+	if (d.DimY)
+		LU0 += (d.Fw[1][o - d.sY] - d.Fw[1][o]) * d._dy;
+	if (d.DimZ)
+		LU0 += (d.Fw[2][o - d.sZ] - d.Fw[2][o]) * d._dz;
+	return LU0;
+}
+template <int E>
+__global__ void __launch_bounds__(256) k_lu(XfDev d, double *__restrict__ LU)
+{
+	long long id;
+	if (!inner_cell(d, id))
+		return;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		LU[n * d.N + id] = lu_of(d, n * d.N + id);
+}
+__device__ __forceinline__ double rk_of(double U, double U1, double LU, double dt, int flag)
+{
+	if (flag == 1)
+		return U + dt * LU;
+	if (flag == 2)
+		return 0.75 * U + 0.25 * U1 + 0.25 * dt * LU;
+	return (U + 2.0 * U1 + 2.0 * dt * LU) * (1.0 / 3.0);
+}
+// dt_dev != nullptr: read dt from the device (graph-replayable); guard: check UI (U1,U1,U for flag 1,2,3) and LU
+template <int E, bool FUSED_LU>
+__global__ void __launch_bounds__(256) k_rk(XfDev d, double *__restrict__ U, double *__restrict__ U1, const double *__restrict__ LU,
+											double dt_host, const double *__restrict__ dt_dev, int flag, int guard)
+{
+	long long id;
+	if (!inner_cell(d, id))
+		return;
+	const double dt = dt_dev ? *dt_dev : dt_host;
+	bool bad = false;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+	{
+		const long long o = n * d.N + id;
+		const double lu = FUSED_LU ? lu_of(d, o) : LU[o];
+		const double u0 = U[o];
+		const double u1 = (flag == 1) ? 0.0 : U1[o];
+		if (guard)
+		{
+			const double ui = (flag == 3) ? u0 : ((flag == 1) ? U1[o] : u1);
+			bad = bad || isnan(ui) || isinf(ui) || isnan(lu) || isinf(lu) || (n == 0 && ui < 0);
+		}
+		const double r = rk_of(u0, u1, lu, dt, flag);
+		if (flag == 3)
+			U[o] = r;
+		else
+			U1[o] = r;
+	}
+	if (guard && bad)
+		d.err[2] = 1;
+}
+template <int E>
+__global__ void __launch_bounds__(256) k_nan(XfDev d, const double *__restrict__ UI, const double *__restrict__ LU)
+{
+	long long id;
+	if (!inner_cell(d, id))
+		return;
+	bool bad = UI[id] < 0;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+	{
+		const double a = UI[n * d.N + id], b = LU[n * d.N + id];
+		bad = bad || isnan(a) || isinf(a) || isnan(b) || isinf(b);
+	}
+	if (bad)
+		d.err[2] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_bc: FluidBCKernel{X,Y,Z} (BCs_kernels.hpp:9-258) launched as in BCs_block.cpp:81-213: one thread per ghost
+// index g < Bw and transverse position, handling the min face then the max face.  BC_COPY faces are skipped
+// (filled by the halo exchange).
+// ---------------------------------------------------------------------------------------------
+template <int E, int DIR>
+__device__ __forceinline__ void bc_apply(const XfDev &d, double *__restrict__ U, int BC, int i, int j, int k,
+										 int mirror_offset, int index_inner, int sign, bool cop)
+{
+	const int Bw = DIR == 0 ? d.Bx : (DIR == 1 ? d.By : d.Bz);
+	const int inner = DIR == 0 ? d.Xi : (DIR == 1 ? d.Yi : d.Zi);
+	const int g = DIR == 0 ? i : (DIR == 1 ? j : k);
+	const long long id = ((long long)k * d.Ymax + j) * d.Xp + i;
+	auto tid = [&](int t) -> long long
+	{ return DIR == 0 ? ((long long)k * d.Ymax + j) * d.Xp + t : (DIR == 1 ? ((long long)k * d.Ymax + t) * d.Xp + i : ((long long)t * d.Ymax + j) * d.Xp + i); };
+	switch (BC)
+	{
+	case 2:
+	{ // Symmetry
+		const long long t = tid(2 * (Bw + mirror_offset) - 1 - g);
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			U[n * d.N + id] = (n == 1 + DIR) ? -U[n * d.N + t] : U[n * d.N + t];
+	}
+	break;
+	case 3:
+	{ // Periodic
+		const long long t = tid(g + sign * inner);
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			U[n * d.N + id] = U[n * d.N + t];
+	}
+	break;
+	case 1:
+	{ // Outflow
+		const long long t = tid(index_inner);
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			U[n * d.N + id] = U[n * d.N + t];
+	}
+	break;
+	case 4:
+	case 5:
+	case 6:
+	{ // nslipWall everywhere; viscWall / slipWall in X only (no-ops in Y,Z: BCs_kernels.hpp:167-171,242-246)
+		if (BC != 4 && DIR != 0)
+			break;
+		const long long t = tid(2 * (Bw + mirror_offset) - 1 - g);
+#pragma unroll
+		for (int n = 0; n < E; n++)
+		{
+			if (n >= 5 && !cop)
+				continue;
+			U[n * d.N + id] = (n >= 1 && n <= 3) ? -U[n * d.N + t] : U[n * d.N + t];
+		}
+	}
+	break;
+	default: // Inflow, innerBlock, BC_COPY
+		break;
+	}
+}
+template <int E, int DIR>
+__global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int bc_min, int bc_max, int cop)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k, g;
+	if constexpr (DIR == 0)
+	{ // threads over (j,k) x g ; g fastest is pointless for coalescing here, ghost columns are 4 wide
+		g = int(t % d.Bx);
+		const long long r = t / d.Bx;
+		j = int(r % d.Ymax), k = int(r / d.Ymax);
+		if (k >= d.Zmax)
+			return;
+		bc_apply<E, 0>(d, U, bc_min, g, j, k, 0, d.Bx, 1, cop);
+		bc_apply<E, 0>(d, U, bc_max, g + d.Xmax - d.Bx, j, k, d.Xi, d.Xmax - d.Bx - 1, -1, cop);
+	}
+	else if constexpr (DIR == 1)
+	{
+		i = int(t % d.Xmax);
+		const long long r = t / d.Xmax;
+		g = int(r % d.By), k = int(r / d.By);
+		if (k >= d.Zmax)
+			return;
+		bc_apply<E, 1>(d, U, bc_min, i, g, k, 0, d.By, 1, cop);
+		bc_apply<E, 1>(d, U, bc_max, i, g + d.Ymax - d.By, k, d.Yi, d.Ymax - d.By - 1, -1, cop);
+	}
+	else
+	{
+		i = int(t % d.Xmax);
+		const long long r = t / d.Xmax;
+		j = int(r % d.Ymax), g = int(r / d.Ymax);
+		if (g >= d.Bz)
+			return;
+		bc_apply<E, 2>(d, U, bc_min, i, j, g, 0, d.Bz, 1, cop);
+		bc_apply<E, 2>(d, U, bc_max, i, j, g + d.Zmax - d.Bz, d.Zi, d.Zmax - d.Bz - 1, -1, cop);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout kernels: reference AoS [cell][E] (unpadded) <-> SoA [E][cell] (x-padded), staged through shared memory so
+// that both sides are coalesced; scalar arrays padded/unpadded; z-slab halo pack/unpack.
+// ---------------------------------------------------------------------------------------------
+template <int E, bool TO_SOA>
+__global__ void __launch_bounds__(128) k_layout(XfDev d, double *__restrict__ soa, double *__restrict__ aos)
+{
+	__shared__ double tile[128 * E];
+	const long long row = blockIdx.y;                 // k*Ymax + j
+	const int i0 = blockIdx.x * 128;
+	const int ni = min(128, d.Xmax - i0);
+	const long long abase = (row * d.Xmax + i0) * E;  // AoS doubles
+	const long long sbase = row * d.Xp + i0;
+	if (TO_SOA)
+	{
+		for (int q = threadIdx.x; q < ni * E; q += 128)
+			tile[q] = aos[abase + q];
+		__syncthreads();
+		if ((int)threadIdx.x < ni)
+#pragma unroll
+			for (int n = 0; n < E; n++)
+				soa[n * d.N + sbase + threadIdx.x] = tile[threadIdx.x * E + n];
+	}
+	else
+	{
+		if ((int)threadIdx.x < ni)
+#pragma unroll
+			for (int n = 0; n < E; n++)
+				tile[threadIdx.x * E + n] = soa[n * d.N + sbase + threadIdx.x];
+		__syncthreads();
+		for (int q = threadIdx.x; q < ni * E; q += 128)
+			aos[abase + q] = tile[q];
+	}
+}
+__global__ void k_scalar_pad(XfDev d, double *__restrict__ padded, double *__restrict__ flat, int to_padded)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = int(t % d.Xmax);
+	const long long row = t / d.Xmax;
+	if (row >= (long long)d.Ymax * d.Zmax)
+		return;
+	if (to_padded)
+		padded[row * d.Xp + i] = flat[t];
+	else
+		flat[t] = padded[row * d.Xp + i];
+}
+// halo buffer layout: [E][Bz planes][Ymax][Xp] ; face 4: inner planes Bz..2Bz-1 (pack) / ghosts 0..Bz-1 (unpack),
+// face 5: inner planes Zmax-2Bz..Zmax-Bz-1 (pack) / ghosts Zmax-Bz..Zmax-1 (unpack)
+template <int E>
+__global__ void __launch_bounds__(256) k_halo(XfDev d, double *__restrict__ U, double *__restrict__ buf, int k0, int pack)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long slab = (long long)d.Bz * d.sZ;
+	if (t >= slab)
+		return;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+	{
+		if (pack)
+			buf[n * slab + t] = U[n * d.N + (long long)k0 * d.sZ + t];
+		else
+			U[n * d.N + (long long)k0 * d.sZ + t] = buf[n * slab + t];
+	}
+}
+
+// =================================================================================================
+//  launchers (C++ linkage inside the namespace; selected at run time by the C-ABI layer)
+// =================================================================================================
+#define XF_CHECK_LAUNCH()                         \
+	do                                            \
+	{                                             \
+		cudaError_t e__ = cudaGetLastError();     \
+		if (e__ != cudaSuccess)                   \
+			return (int)e__;                      \
+	} while (0)
+
+template <class C>
+static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s)
+{
+	const long long nb = (d.N + 127) / 128;
+	k_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, U, flags);
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+
+template <class C, int DIR, int WENO>
+static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
+{
+	constexpr int E = C::E, NST = XfStencil<WENO>::NST;
+	static bool attr_done = false;
+	if constexpr (DIR == 0)
+	{
+		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
+		if (!attr_done)
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
+		const long long ncell = (long long)d.Zi * d.sZ;
+		k_sweep<C, DIR, WENO><<<(unsigned)((ncell + XF_TX - 1) / XF_TX), XF_TX, smem, s>>>(d, U, d.Fw[0]);
+	}
+	else
+	{
+		constexpr size_t smem = size_t(2 * E + 3) * (XF_TF + NST - 1) * XF_TW * sizeof(double);
+		if (!attr_done)
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
+		dim3 g;
+		g.x = (d.Xi + XF_TW - 1) / XF_TW;
+		if (DIR == 1)
+			g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = d.Zi;
+		else
+			g.y = d.Yi, g.z = (d.Zi + 1 + XF_TF - 1) / XF_TF;
+		k_sweep<C, DIR, WENO><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR]);
+	}
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+template <class C>
+static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches)
+{
+	int rc = 0;
+	if (d.weno == 7)
+	{
+		if (d.DimX) rc |= sweep_t<C, 0, 7>(d, U, s), ++*launches;
+		if (d.DimY) rc |= sweep_t<C, 1, 7>(d, U, s), ++*launches;
+		if (d.DimZ) rc |= sweep_t<C, 2, 7>(d, U, s), ++*launches;
+	}
+	else
+	{
+		if (d.DimX) rc |= sweep_t<C, 0, 5>(d, U, s), ++*launches;
+		if (d.DimY) rc |= sweep_t<C, 1, 5>(d, U, s), ++*launches;
+		if (d.DimZ) rc |= sweep_t<C, 2, 5>(d, U, s), ++*launches;
+	}
+	return rc;
+}
+
+#define XF_DISPATCH_CFG(ns, cop, ...)                          \
+	if (!(cop)) { using C = XfCfg<1, false>; __VA_ARGS__; }    \
+	else if ((ns) == 2) { using C = XfCfg<2, true>; __VA_ARGS__; } \
+	else if ((ns) == 3) { using C = XfCfg<3, true>; __VA_ARGS__; } \
+	else if ((ns) == 4) { using C = XfCfg<4, true>; __VA_ARGS__; } \
+	else if ((ns) == 5) { using C = XfCfg<5, true>; __VA_ARGS__; } \
+	else return -1;
+
+#define XF_DISPATCH_E(E_, ...)                          \
+	switch (E_)                                         \
+	{                                                   \
+	case 5: { constexpr int E = 5; __VA_ARGS__; } break; \
+	case 6: { constexpr int E = 6; __VA_ARGS__; } break; \
+	case 7: { constexpr int E = 7; __VA_ARGS__; } break; \
+	case 8: { constexpr int E = 8; __VA_ARGS__; } break; \
+	case 9: { constexpr int E = 9; __VA_ARGS__; } break; \
+	default: return -1;                                 \
+	}
+
+int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s)
+{
+	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s));
+}
+int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches)
+{
+	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches));
+}
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+int launch_lu(const XfDev &d, int E_, double *LU, cudaStream_t s)
+{
+	const long long n = (long long)d.Xi * d.Yi * d.Zi;
+	XF_DISPATCH_E(E_, k_lu<E><<<nblk(n, 256), 256, 0, s>>>(d, LU));
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_rk(const XfDev &d, int E_, double *U, double *U1, const double *LU, double dt, const double *dt_dev, int flag, int guard, int fused, cudaStream_t s)
+{
+	const long long n = (long long)d.Xi * d.Yi * d.Zi;
+	if (fused)
+	{
+		XF_DISPATCH_E(E_, k_rk<E, true><<<nblk(n, 256), 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
+	}
+	else
+	{
+		XF_DISPATCH_E(E_, k_rk<E, false><<<nblk(n, 256), 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
+	}
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_nan(const XfDev &d, int E_, const double *UI, const double *LU, cudaStream_t s)
+{
+	const long long n = (long long)d.Xi * d.Yi * d.Zi;
+	XF_DISPATCH_E(E_, k_nan<E><<<nblk(n, 256), 256, 0, s>>>(d, UI, LU));
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_bc(const XfDev &d, int E_, int cop, double *U, const int bc[6], cudaStream_t s, long long *launches)
+{
+	if (d.DimX && !(bc[0] == 0 && bc[1] == 0))
+	{
+		const long long n = (long long)d.Bx * d.Ymax * d.Zmax;
+		XF_DISPATCH_E(E_, k_bc<E, 0><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[0], bc[1], cop));
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
+	if (d.DimY)
+	{
+		const long long n = (long long)d.Xmax * d.By * d.Zmax;
+		XF_DISPATCH_E(E_, k_bc<E, 1><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[2], bc[3], cop));
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
+	if (d.DimZ)
+	{
+		const long long n = (long long)d.Xmax * d.Ymax * d.Bz;
+		XF_DISPATCH_E(E_, k_bc<E, 2><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[4], bc[5], cop));
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
+	return 0;
+}
+int launch_dt(const XfDev &d, const double *rho, cudaStream_t s)
+{
+	k_dt<<<nblk(d.N, 256), 256, 0, s>>>(d, rho);
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_dt_final(const XfDev &d, double t_end, cudaStream_t s)
+{
+	k_dt_final<<<1, 1, 0, s>>>(d, t_end);
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_layout(const XfDev &d, int E_, double *soa, double *aos, int to_soa, cudaStream_t s)
+{
+	dim3 g((d.Xmax + 127) / 128, (unsigned)((long long)d.Ymax * d.Zmax));
+	if (to_soa)
+	{
+		XF_DISPATCH_E(E_, k_layout<E, true><<<g, 128, 0, s>>>(d, soa, aos));
+	}
+	else
+	{
+		XF_DISPATCH_E(E_, k_layout<E, false><<<g, 128, 0, s>>>(d, soa, aos));
+	}
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_scalar_pad(const XfDev &d, double *padded, double *flat, int to_padded, cudaStream_t s)
+{
+	const long long n = (long long)d.Xmax * d.Ymax * d.Zmax;
+	k_scalar_pad<<<nblk(n, 256), 256, 0, s>>>(d, padded, flat, to_padded);
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+int launch_halo(const XfDev &d, int E_, double *U, double *buf, int k0, int pack, cudaStream_t s)
+{
+	const long long n = (long long)d.Bz * d.sZ;
+	XF_DISPATCH_E(E_, k_halo<E><<<nblk(n, 256), 256, 0, s>>>(d, U, buf, k0, pack));
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+
+} // namespace XF_NS

@@ -1,0 +1,522 @@
+// xf_math.cuh -- device math of the inviscid path: NASA-9 thermo + limited Newton T(e,Y), WENO5-JS / WENO7-JS,
+// Roe-averaged multi-species sound speed and the characteristic flux at one face.
+//
+// Written for FP64 on sm_100a.  Every expression keeps the reference's association order, so that the
+// strict build (-fmad=false) performs the same sequence of IEEE-754 roundings as the reference CPU path;
+// the only places where bits can differ are libdevice log() vs glibc log().  Structural zeros / +-1 of
+// the eigenvector matrices are exploited (x*0 and +0 are exact no-ops, *1 and *-1 are exact), which is
+// where this differs from the reference's dense Emax x Emax loops (Eigen_callback.h:194-230).
+//
+// Reference files followed: solver_Ini/Thermo_device.h, solver_Ini/Mixing_device.h,
+// solver_Reconstruction/schemes/WENO{5,7}s_schemes.hpp, FDM_Method/positive-definite_eigen/
+// {Utils_device.hpp,Eigen_matrix.hpp,Eigen_callback.h}, include/global_marco.h.
+#pragma once
+#include "xf_types.h"
+
+#define XF_DEV __device__ __forceinline__
+
+template <int NS_, bool COP_>
+struct XfCfg
+{
+	static constexpr int NS = NS_;
+	static constexpr bool COP = COP_;
+	static constexpr int E = COP_ ? NS_ + 4 : 5;   // Emax
+	static constexpr int NC = COP_ ? NS_ - 1 : 0;  // NUM_COP
+};
+
+// sycl::min / sycl::max semantics of the host path: (b < a) ? b : a  /  (a < b) ? b : a
+XF_DEV double xf_min(double a, double b) { return (b < a) ? b : a; }
+XF_DEV double xf_max(double a, double b) { return (a < b) ? b : a; }
+
+// ------------------------------------------------------------------------------------------------
+// NASA-9 species thermo (Thermo_device.h:10-23, 62-80)
+// ------------------------------------------------------------------------------------------------
+template <int R>
+XF_DEV double xf_cp_r(const XfThermo &th, int n, double T, double _T)
+{
+	const double *a = th.ccoef[R][n];
+	return th.Ri[n] * ((a[0] * _T + a[1]) * _T + a[2] + (a[3] + (a[4] + (a[5] + a[6] * T) * T) * T) * T);
+}
+template <int R>
+XF_DEV double xf_h_r(const XfThermo &th, int n, double T, double lnT)
+{
+	const double *h = th.hcoef[R][n];
+	return th.Ri[n] * (h[0] / T + h[1] * lnT + (h[2] + (h[3] + (h[4] + (h[5] + h[6] * T) * T) * T) * T) * T + h[7]);
+}
+XF_DEV int xf_range(double T) { return (T >= 1000.0 && T < 6000.0) ? 1 : ((T < 1000.0) ? 0 : 2); }
+
+// mixture Cp at T0 (get_CopCp, Mixing_device.h:61-68)
+template <class C>
+XF_DEV double xf_mix_cp(const XfThermo &th, const double *yi, double T0)
+{
+	const double T = xf_max(T0, 200.0), _T = 1.0 / T;
+	const int r = xf_range(T);
+	double cp = 0.0;
+	if (r == 0)
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			cp += yi[n] * xf_cp_r<0>(th, n, T, _T);
+	}
+	else if (r == 1)
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			cp += yi[n] * xf_cp_r<1>(th, n, T, _T);
+	}
+	else
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			cp += yi[n] * xf_cp_r<2>(th, n, T, _T);
+	}
+	return cp;
+}
+// species enthalpies at T0 into hi[] (get_Enthalpy_NASA incl. the linear extension below 200 K)
+template <class C>
+XF_DEV void xf_species_h(const XfThermo &th, double T0, double *hi)
+{
+	const double T = xf_max(T0, 200.0), lnT = log(T);
+	const int r = xf_range(T);
+	if (r == 0)
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			hi[n] = xf_h_r<0>(th, n, T, lnT);
+	}
+	else if (r == 1)
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			hi[n] = xf_h_r<1>(th, n, T, lnT);
+	}
+	else
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			hi[n] = xf_h_r<2>(th, n, T, lnT);
+	}
+	if (T0 < 200.0)
+	{
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			hi[n] += xf_cp_r<0>(th, n, 200.0, 1.0 / 200.0) * (T0 - 200.0);
+	}
+}
+
+// limited Newton iteration for T from internal energy (get_T / sub_FuncT, Mixing_device.h:159-193).
+// R = get_CopR(yi) is loop-invariant and passed in.
+template <class C>
+XF_DEV double xf_get_T(const XfThermo &th, const double *yi, double e, double T0, double R)
+{
+	double T = T0;
+	for (int it = 1; it < 101; it++)
+	{
+		double hi[C::NS];
+		xf_species_h<C>(th, T, hi);
+		double h = 0.0;
+#pragma unroll
+		for (int n = 0; n < C::NS; n++)
+			h += hi[n] * yi[n];
+		const double Cp = xf_mix_cp<C>(th, yi, T);
+		const double func_T = h - R * T - e;
+		const double dfunc_T = Cp - R;
+		double df = xf_min(func_T / (dfunc_T + 1.0e-30), 1e-3 * T);
+		df = xf_max(df, -1e-2 * T);
+		T = T - df;
+		if (fabs(df) <= 1.0e-6)
+			break;
+	}
+	return T;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WENO5-JS as written in weno5old_BODY (WENO5s_schemes.hpp:12-69) and WENO7-JS (WENO7s_schemes.hpp:8-128)
+// ------------------------------------------------------------------------------------------------
+XF_DEV double xf_weno5_body(double v1, double v2, double v3, double v4, double v5)
+{
+	double a1, a2, a3;
+	a1 = v1 - 2.0 * v2 + v3;
+	double s1 = 13.0 * a1 * a1;
+	a1 = v1 - 4.0 * v2 + 3.0 * v3;
+	s1 += 3.0 * a1 * a1;
+	a1 = v2 - 2.0 * v3 + v4;
+	double s2 = 13.0 * a1 * a1;
+	a1 = v2 - v4;
+	s2 += 3.0 * a1 * a1;
+	a1 = v3 - 2.0 * v4 + v5;
+	double s3 = 13.0 * a1 * a1;
+	a1 = 3.0 * v3 - 4.0 * v4 + v5;
+	s3 += 3.0 * a1 * a1;
+	s1 += 1.0E-6, s2 += 1.0E-6, s3 += 1.0E-6;
+	a1 = 0.1 * s2 * s2 * s3 * s3;
+	a2 = 0.6 * s1 * s1 * s3 * s3;
+	a3 = 0.3 * s1 * s1 * s2 * s2;
+	const double tw1 = 1.0 / (a1 + a2 + a3);
+	a1 = a1 * tw1, a2 = a2 * tw1, a3 = a3 * tw1;
+	s1 = a1 * (2.0 * v1 - 7.0 * v2 + 11.0 * v3);
+	s2 = a2 * (-v2 + 5.0 * v3 + 2.0 * v4);
+	s3 = a3 * (2.0 * v3 + 5.0 * v4 - v5);
+	return (s1 + s2 + s3);
+}
+XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v5, double v6, double v7)
+{
+	const double ep = 1.0e-7;
+	const double C0 = 1.0 / 35.0, C1 = 12.0 / 35.0, C2 = 18.0 / 35.0, C3 = 4.0 / 35.0;
+	const double S10 = -2.0 / 6.0 * v1 + 9.0 / 6.0 * v2 - 18.0 / 6.0 * v3 + 11.0 / 6.0 * v4;
+	const double S11 = 1.0 / 6.0 * v2 - 6.0 / 6.0 * v3 + 3.0 / 6.0 * v4 + 2.0 / 6.0 * v5;
+	const double S12 = -2.0 / 6.0 * v3 - 3.0 / 6.0 * v4 + 6.0 / 6.0 * v5 - 1.0 / 6.0 * v6;
+	const double S13 = -11.0 / 6.0 * v4 + 18.0 / 6.0 * v5 - 9.0 / 6.0 * v6 + 2.0 / 6.0 * v7;
+	const double S20 = -v1 + 4.0 * v2 - 5.0 * v3 + 2.0 * v4;
+	const double S21 = v3 - 2.0 * v4 + v5;
+	const double S22 = v4 - 2.0 * v5 + v6;
+	const double S23 = 2.0 * v4 - 5.0 * v5 + 4.0 * v6 - 1.0 * v7;
+	const double S30 = -v1 + 3.0 * v2 - 3.0 * v3 + v4;
+	const double S31 = -v2 + 3.0 * v3 - 3.0 * v4 + v5;
+	const double S32 = -v3 + 3.0 * v4 - 3.0 * v5 + v6;
+	const double S33 = -v4 + 3.0 * v5 - 3.0 * v6 + v7;
+	const double S0 = S10 * S10 + 13.0 / 12.0 * S20 * S20 + 1043.0 / 960.0 * S30 * S30 + 1.0 / 12.0 * S10 * S30;
+	const double S1 = S11 * S11 + 13.0 / 12.0 * S21 * S21 + 1043.0 / 960.0 * S31 * S31 + 1.0 / 12.0 * S11 * S31;
+	const double S2 = S12 * S12 + 13.0 / 12.0 * S22 * S22 + 1043.0 / 960.0 * S32 * S32 + 1.0 / 12.0 * S12 * S32;
+	const double S3 = S13 * S13 + 13.0 / 12.0 * S23 * S23 + 1043.0 / 960.0 * S33 * S33 + 1.0 / 12.0 * S13 * S33;
+	const double a0 = C0 / ((ep + S0) * (ep + S0));
+	const double a1 = C1 / ((ep + S1) * (ep + S1));
+	const double a2 = C2 / ((ep + S2) * (ep + S2));
+	const double a3 = C3 / ((ep + S3) * (ep + S3));
+	const double sum = a0 + a1 + a2 + a3;
+	const double W0 = a0 / sum, W1 = a1 / sum, W2 = a2 / sum, W3 = a3 / sum;
+	const double q0 = -3.0 / 12.0 * v1 + 13.0 / 12.0 * v2 - 23.0 / 12.0 * v3 + 25.0 / 12.0 * v4;
+	const double q1 = 1.0 / 12.0 * v2 - 5.0 / 12.0 * v3 + 13.0 / 12.0 * v4 + 3.0 / 12.0 * v5;
+	const double q2 = -1.0 / 12.0 * v3 + 7.0 / 12.0 * v4 + 7.0 / 12.0 * v5 - 1.0 / 12.0 * v6;
+	const double q3 = 3.0 / 12.0 * v4 + 13.0 / 12.0 * v5 - 5.0 / 12.0 * v6 + 1.0 / 12.0 * v7;
+	return W0 * q0 + W1 * q1 + W2 * q2 + W3 * q3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Roe state at a face (MARCO_ROE global_marco.h:26-34, ReconstructSoundSpeed Utils_device.hpp:102-140,
+// SoundSpeedMultiSpecies :42-79, MARCO_NOCOPC2 / MARCO_PREEIGEN Eigen_callback.h:87-106)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+struct XfRoe
+{
+	double u, v, w, H, c, c1, b1, b2, b3;
+	double z[C::NC > 0 ? C::NC : 1], y[C::NC > 0 ? C::NC : 1];
+};
+
+// per-cell face-side inputs gathered from the work arrays
+template <class C>
+struct XfSide
+{
+	double rho, u, v, w, H, p;
+	double g3, dpdrho, e, prho;                                    // COP only
+	double y[C::NC > 0 ? C::NC : 1], dpdrhoi[C::NC > 0 ? C::NC : 1]; // COP only
+};
+
+template <class C>
+XF_DEV void xf_roe_state(const XfSide<C> &l, const XfSide<C> &r, double gamma0, XfRoe<C> &R)
+{
+	const double D = sqrt(r.rho / l.rho);
+	const double D1 = 1.0 / (D + 1.0);
+	R.u = (l.u + D * r.u) * D1;
+	R.v = (l.v + D * r.v) * D1;
+	R.w = (l.w + D * r.w) * D1;
+	R.H = (l.H + D * r.H) * D1;
+	const double _P = (l.p + D * r.p) * D1;
+	const double _rho = sqrt(r.rho * l.rho);
+	double c2, b1, b3;
+	if constexpr (C::COP)
+	{
+		constexpr int NC = C::NC;
+		double dpi[NC > 0 ? NC : 1], drhoi[NC > 0 ? NC : 1];
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+			R.y[n] = (l.y[n] + D * r.y[n]) * D1;
+		const double Gamma = (l.g3 + D * r.g3) * D1;
+		const double _dpdrho = (l.dpdrho + D * r.dpdrho) * D1;
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+		{
+			dpi[n] = (l.dpdrhoi[n] + D * r.dpdrhoi[n]) * D1;
+			drhoi[n] = r.rho * r.y[n] - l.rho * l.y[n];
+		}
+		const double du = r.u - l.u, dv = r.v - l.v, dw = r.w - l.w;
+		const double _prho = (l.prho + D * r.prho) * D1 + 0.5 * D * D1 * D1 * (du * du + dv * dv + dw * dw);
+		const double _dpdE = ((l.g3 - 1.0) + D * (r.g3 - 1.0)) * D1;
+		const double _dpde = ((l.g3 - 1.0) * l.rho + D * ((r.g3 - 1.0) * r.rho)) * D1;
+		const double dp = r.p - l.p, drho = r.rho - l.rho, de = r.e - l.e;
+		// SoundSpeedMultiSpecies
+		double Sum_dpdrhoi = 0.0, Sum_dpdrhoi2 = 0.0, Sum_Yidpdrhoi = 0.0;
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+		{
+			Sum_dpdrhoi += dpi[n] * drhoi[n];
+			Sum_dpdrhoi2 += dpi[n] * drhoi[n] * dpi[n] * drhoi[n];
+		}
+		const double temp1 = dp - (_dpdrho * drho + _dpde * de + Sum_dpdrhoi);
+		const double temp = temp1 / (_dpdrho * _dpdrho * drho * drho + _dpde * de * _dpde * de + Sum_dpdrhoi2 + 1e-19);
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+			Sum_Yidpdrhoi += R.y[n] * dpi[n];
+		const double _dpdE_new = _dpdE + _dpdE * _dpdE * de * _rho * temp;
+		const double _dpdrho_new = _dpdrho + _dpdrho * _dpdrho * drho * temp;
+		const double csqr = _dpdrho_new + _dpdE_new * _prho + Sum_Yidpdrhoi;
+		b1 = _dpdE_new / csqr;
+		b3 = 0.0;
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+		{
+			const double dpn = dpi[n] + dpi[n] * dpi[n] * drhoi[n] * temp;
+			R.z[n] = -dpn / _dpdE_new;
+			b3 += R.y[n] * R.z[n];
+		}
+		b3 *= b1;
+		// c2 <= 0 fallback: Gamma * P * rho (a product, as written; Utils_device.hpp:136-137)
+		const double c2w = (0.0 < csqr) ? 0.0 : 1.0;
+		c2 = Gamma * _P * _rho * c2w + (1.0 - c2w) * csqr;
+	}
+	else
+	{
+		c2 = gamma0 * _P / _rho;
+		b1 = (gamma0 - 1.0) / c2;
+		b3 = 0.0;
+	}
+	const double q2 = R.u * R.u + R.v * R.v + R.w * R.w;
+	R.c = sqrt(c2);
+	R.b1 = b1, R.b3 = b3;
+	R.b2 = 1.0 + b1 * q2 - b1 * R.H;
+	R.c1 = 1.0 / R.c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Characteristic-wise split flux at one face (MARCO_FLUXWALL_WENO5/7, Eigen_callback.h:127-230, with the
+// rows of L / columns of R from Eigen_matrix.hpp:7-455).
+//
+// ST is a stencil accessor: ST::U(s,n), ST::F(s,n) conserved variable / physical flux component n of
+// stencil cell s (s = 0..NST-1 <-> offset m = s-P along the sweep), ST::lam(s,t) = |u_d - c|, |u_d|,
+// |u_d + c| (t = 0,1,2) of that cell.  Face lies between s = P and s = P+1.
+// ------------------------------------------------------------------------------------------------
+template <int WENO>
+struct XfStencil
+{
+	static constexpr int P = WENO == 7 ? 3 : 2;    // cells left of the face's left cell
+	static constexpr int NST = WENO == 7 ? 8 : 6;  // cells actually used by the reconstruction
+};
+
+template <class C, int DIR, int WENO, class ST>
+XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const double *glf /*3*/, double *Fw /*E*/)
+{
+	constexpr int E = C::E, NC = C::NC, NST = XfStencil<WENO>::NST;
+	constexpr int ENT = DIR + 1; // row/column index of the entropy wave: x 1, y 2, z 3
+	const double un = DIR == 0 ? R.u : (DIR == 1 ? R.v : R.w);
+	const double un_c = un * R.c1;
+	const double b1 = R.b1, b2 = R.b2, b3 = R.b3, c1 = R.c1;
+
+	double f[E];
+#pragma unroll
+	for (int n = 0; n < E; n++)
+	{
+		// ---- artificial viscosity for this field (Eigen_callback.h:134-145, 188-193) ----
+		const int t = (n == 0) ? 0 : ((n == E - 1) ? 2 : 1);
+		const double ev = (n == 0) ? fabs(un - R.c) : ((n == E - 1) ? fabs(un + R.c) : fabs(un));
+		double av;
+		if (alpha == 1)
+			av = ev;
+		else if (alpha == 2)
+		{
+			if constexpr (WENO == 7)
+				av = ev; // eigen_local == 0 for SCHEME_ORDER 7 (Eigen_value.hpp:29-32): the sign test never fires
+			else
+			{
+				double m = 0.0;
+#pragma unroll
+				for (int s = 0; s < NST; s++)
+					m = xf_max(m, st.lam(s, t));
+				av = m;
+			}
+		}
+		else
+			av = glf[t];
+
+		// ---- project the stencil on row n of L ----
+		double uf[NST], ff[NST];
+		if (n == 0 || n == E - 1 || n == ENT)
+		{
+			double l[E];
+			if (n == ENT)
+			{
+				l[0] = (1.0 - b2 - b3) / b1;
+				l[1] = R.u, l[2] = R.v, l[3] = R.w, l[4] = -1.0;
+#pragma unroll
+				for (int m = 0; m < NC; m++)
+					l[5 + m] = R.z[m];
+			}
+			else if (n == 0)
+			{
+				l[0] = 0.5 * (b2 + un_c + b3);
+				l[1] = DIR == 0 ? -0.5 * (b1 * R.u + c1) : -0.5 * (b1 * R.u);
+				l[2] = DIR == 1 ? -0.5 * (b1 * R.v + c1) : -0.5 * (b1 * R.v);
+				l[3] = DIR == 2 ? -0.5 * (b1 * R.w + c1) : -0.5 * (b1 * R.w);
+				l[4] = 0.5 * b1;
+#pragma unroll
+				for (int m = 0; m < NC; m++)
+					l[5 + m] = -0.5 * b1 * R.z[m];
+			}
+			else
+			{
+				l[0] = 0.5 * (b2 - un_c + b3);
+				l[1] = DIR == 0 ? 0.5 * (-b1 * R.u + c1) : 0.5 * (-b1 * R.u);
+				l[2] = DIR == 1 ? 0.5 * (-b1 * R.v + c1) : 0.5 * (-b1 * R.v);
+				l[3] = DIR == 2 ? 0.5 * (-b1 * R.w + c1) : 0.5 * (-b1 * R.w);
+				l[4] = 0.5 * b1;
+#pragma unroll
+				for (int m = 0; m < NC; m++)
+					l[5 + m] = -0.5 * b1 * R.z[m];
+			}
+#pragma unroll
+			for (int s = 0; s < NST; s++)
+			{
+				uf[s] = st.U(s, 0) * l[0];
+				ff[s] = st.F(s, 0) * l[0];
+			}
+#pragma unroll
+			for (int k = 1; k < E; k++)
+			{
+				if (n == ENT && k == 4)
+				{ // * (-1.0)
+#pragma unroll
+					for (int s = 0; s < NST; s++)
+					{
+						uf[s] = uf[s] - st.U(s, 4);
+						ff[s] = ff[s] - st.F(s, 4);
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int s = 0; s < NST; s++)
+					{
+						uf[s] = uf[s] + st.U(s, k) * l[k];
+						ff[s] = ff[s] + st.F(s, k) * l[k];
+					}
+				}
+			}
+		}
+		else if (n >= 1 && n <= 3)
+		{ // shear rows: two non-zero entries, one of them +-1 (Eigen_matrix.hpp:38-59,177-209,327-348)
+			// x: n=2 (v,-e2) n=3 (-w,+e3);  y: n=1 (-u,+e1) n=3 (w,-e3);  z: n=1 (u,-e1) n=2 (-v,+e2)
+			const double vel = (n == 1) ? R.u : ((n == 2) ? R.v : R.w);
+			const bool plus_unit = (DIR == 0) ? (n == 3) : ((DIR == 1) ? (n == 1) : (n == 2));
+#pragma unroll
+			for (int s = 0; s < NST; s++)
+			{
+				if (plus_unit)
+				{ // U0*(-vel) + Un
+					uf[s] = st.U(s, 0) * (-vel) + st.U(s, n);
+					ff[s] = st.F(s, 0) * (-vel) + st.F(s, n);
+				}
+				else
+				{ // U0*vel - Un
+					uf[s] = st.U(s, 0) * vel - st.U(s, n);
+					ff[s] = st.F(s, 0) * vel - st.F(s, n);
+				}
+			}
+		}
+		else
+		{ // species rows: (-Y_s, 0,0,0,0, e_s)
+			const double ys = R.y[(n - 4) < NC ? (n - 4) : 0];
+#pragma unroll
+			for (int s = 0; s < NST; s++)
+			{
+				uf[s] = st.U(s, 0) * (-ys) + st.U(s, n + 1);
+				ff[s] = st.F(s, 0) * (-ys) + st.F(s, n + 1);
+			}
+		}
+
+		// ---- Lax-Friedrichs splitting + WENO ----
+		if constexpr (WENO == 7)
+		{
+			double pp[8], mm[8];
+#pragma unroll
+			for (int s = 0; s < 8; s++)
+			{
+				const double au = av * uf[s];
+				pp[s] = 0.5 * (ff[s] + au);
+				mm[s] = 0.5 * (ff[s] - au);
+			}
+			// weno7_P(&pp[3]): f[-3..3]; weno7_M(&mm[3]): k=1, v1=f[4] ... v7=f[-2]
+			f[n] = xf_weno7_body(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6]) +
+				   xf_weno7_body(mm[7], mm[6], mm[5], mm[4], mm[3], mm[2], mm[1]);
+		}
+		else
+		{
+			// stencil s=0..5 <-> cells i-2..i+3 ; weno5old_GPU(&pp[3],&mm[3]): plus uses i-2..i+2, minus i+3..i-1
+			double au[6];
+#pragma unroll
+			for (int s = 0; s < 6; s++)
+				au[s] = av * uf[s];
+			const double p1 = 0.5 * (ff[0] + au[0]), p2 = 0.5 * (ff[1] + au[1]), p3 = 0.5 * (ff[2] + au[2]),
+						 p4 = 0.5 * (ff[3] + au[3]), p5 = 0.5 * (ff[4] + au[4]);
+			const double m1 = 0.5 * (ff[5] - au[5]), m2 = 0.5 * (ff[4] - au[4]), m3 = 0.5 * (ff[3] - au[3]),
+						 m4 = 0.5 * (ff[2] - au[2]), m5 = 0.5 * (ff[1] - au[1]);
+			f[n] = (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
+		}
+		// compiler fence: forbid keeping stencil values loaded for this field alive into the next one
+		// (without it the unrolled field loop is CSE'd into ~2*E*NST live doubles and spills)
+		asm volatile("" ::: "memory");
+	}
+
+	// ---- back-projection Fw[k] = sum_n f[n] * R[n][k], n ascending, from 0.0 (Eigen_callback.h:222-230) ----
+#pragma unroll
+	for (int k = 0; k < E; k++)
+		Fw[k] = 0.0;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+	{
+		const double fn = f[n];
+		if (n == 0 || n == E - 1)
+		{
+			const double sg = (n == 0) ? -1.0 : 1.0; // u -+ c
+			Fw[0] = Fw[0] + fn;
+			Fw[1] = Fw[1] + fn * (DIR == 0 ? (n == 0 ? R.u - R.c : R.u + R.c) : R.u);
+			Fw[2] = Fw[2] + fn * (DIR == 1 ? (n == 0 ? R.v - R.c : R.v + R.c) : R.v);
+			Fw[3] = Fw[3] + fn * (DIR == 2 ? (n == 0 ? R.w - R.c : R.w + R.c) : R.w);
+			Fw[4] = Fw[4] + fn * (n == 0 ? R.H - un * R.c : R.H + un * R.c);
+			(void)sg;
+#pragma unroll
+			for (int m = 0; m < NC; m++)
+				Fw[5 + m] = Fw[5 + m] + fn * R.y[m];
+		}
+		else if (n == ENT)
+		{
+			Fw[0] = Fw[0] + fn * b1;
+			Fw[1] = Fw[1] + fn * (R.u * b1);
+			Fw[2] = Fw[2] + fn * (R.v * b1);
+			Fw[3] = Fw[3] + fn * (R.w * b1);
+			Fw[4] = Fw[4] + fn * (R.H * b1 - 1.0);
+#pragma unroll
+			for (int m = 0; m < NC; m++)
+				Fw[5 + m] = Fw[5 + m] + fn * (b1 * R.y[m]);
+		}
+		else if (n >= 1 && n <= 3)
+		{ // x: n=2 (0,0,-1,0,-v) n=3 (0,0,0,1,w); y: n=1 (0,1,0,0,u) n=3 (0,0,0,-1,-w); z: n=1 (0,-1,0,0,-u) n=2 (0,0,1,0,v)
+			const double vel = (n == 1) ? R.u : ((n == 2) ? R.v : R.w);
+			const bool plus_unit = (DIR == 0) ? (n == 3) : ((DIR == 1) ? (n == 1) : (n == 2));
+			if (plus_unit)
+			{
+				Fw[n] = Fw[n] + fn;
+				Fw[4] = Fw[4] + fn * vel;
+			}
+			else
+			{
+				Fw[n] = Fw[n] - fn;
+				Fw[4] = Fw[4] + fn * (-vel);
+			}
+		}
+		else
+		{ // species column: (0,0,0,0,z_s, e_s)
+			const int s = (n - 4) < NC ? (n - 4) : 0;
+			Fw[4] = Fw[4] + fn * R.z[s];
+			Fw[n + 1] = Fw[n + 1] + fn;
+		}
+	}
+}
