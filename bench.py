@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric (Mcell*stage/s of the inviscid per-RK-stage RHS path) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA path (this repo)
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's own CPU implementation (oracle/_ref)
+
+A "step" is one SSP-RK3 time step = 3 stages of {ghost fill, primitive recovery, x/y/z characteristic WENO sweeps, flux
+divergence + stage update} plus the CFL dt.  Workload (config.workload): BASELINE.json configs[3], the 3-D multi-species
+shock-bubble interaction (Inert-SBI, Emax = 9), WENO5-JS + LLF, 512^3 inner cells per GPU, weak-scaled in z over N GPUs with
+a ghost-plane halo exchange per stage (NCCL send/recv) and a MAX all-reduce of the dt maxima per step.
+
+value      = inner cells of all ranks * 3 * K / (device time of the K steps, max over ranks) / 1e6, state resident in HBM
+e2e        = the same through xf_step_host: every step uploads the AoS state from pinned host memory, runs the step, and
+             downloads the AoS state (what the reference's per-step CopyToUbak does, src/XFLUIDS.cpp:174,644)
+roofline   = the dominant kernel (the slowest directional sweep) against the FP64 FMA rate measured on this device
+cpu_baseline = the unmodified reference (oracle/_ref, OpenMP host shim) on a bounded sample of the same case, rank 0, N = 1
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (settings json, sample grid, reference variant dir, E, NS)
+    "sbi": dict(json="shock-bubble.json", grid=(512, 512, 512), ref="sbi_w5_fast", refcase="sbi", E=9, NS=5, cop=1,
+                desc="shock-bubble.json Inert-SBI 3-D multi-species shock-bubble, WENO5-JS + LLF, inviscid, reactions off"),
+    "jet": dict(json="expanded-jet.json", grid=(1024, 512, 512), ref="jet_w5_fast", refcase="jet", E=7, NS=3, cop=1,
+                desc="expanded-jet.json 3-D under-expanded multi-component jet, WENO5-JS + LLF, inviscid"),
+}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic work model (BASELINE.md section 3 / SURVEY 8d); flop = FP64 add/mul/compare 1, FMA 2, div/sqrt/log 1
+# ---------------------------------------------------------------------------------------------------------------------
+def sweep_flops_per_face(E, NS, cop, weno=5):
+    NC = NS - 1 if cop else 0
+    B = 175 * NS + 40 * NC + 115 if cop else 4
+    return 32 + B + E * (34 * E + 2 * NC + (399 if weno == 7 else 212)) + 6 * E
+
+
+def sweep_bytes_per_cell(E):
+    return (E + 2) * 8 + E * 8  # read U, p, T once; write this direction's flux contribution once
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.p, self.f = index, None, None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])), mx.append(float(t[2])), pw.append(float(t[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation of the path (oracle/_ref, else the oracle port)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_cpu_reference(wl, grid, nsteps, threads):
+    """Runs the unmodified reference (OpenMP host shim build) on `grid` for `nsteps`; returns (Mcell*stage/s, kind, seconds)."""
+    w = WORKLOADS[wl]
+    d = os.path.join(REPO, "oracle", "_ref", w["ref"])
+    exe = os.path.join(d, "XFLUIDS")
+    if os.path.exists(exe):
+        out = os.path.join(d, "output")
+        os.makedirs(os.path.join(out, "cal"), exist_ok=True)
+        for f in os.listdir(out):
+            if "CheckingPoint" in f or "AdaptiveRange" in f:
+                os.remove(os.path.join(out, f))
+        env = dict(os.environ, XF_NSTEPS=str(nsteps), OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
+        env.pop("XF_DUMP_DIR", None)
+        r = subprocess.run([exe, "-run=%d,%d,%d,%d" % (grid[0], grid[1], grid[2], nsteps)], cwd=d, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+        m = re.search(r"ORACLE_TIMING steps=(\d+) seconds=([0-9.eE+-]+) mcell_stage_per_s=([0-9.eE+-]+)", r.stdout)
+        if m and int(m.group(1)) == nsteps:
+            return float(m.group(3)), "reference", float(m.group(2)), threads
+        sys.stderr.write("bench: oracle/_ref run failed, falling back to the oracle port\n" + r.stdout[-500:] + "\n")
+    # the oracle port (single thread): test infrastructure used here only as the timed CPU baseline
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import numpy as np
+    import xfref
+    from xfluids_b200 import host
+    so = os.path.join(REPO, "oracle", "_build", "liboracle_fast.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["bash", os.path.join(REPO, "oracle", "build_oracle.sh")])
+    s = host.Setup(os.path.join(REPO, "settings", w["json"]), ["-run=%d,%d,%d" % tuple(grid), "-weno=5", "-alpha=LLF"])
+    U, T = s.initial_condition()
+    o = xfref.Oracle(w["refcase"], tuple(grid), weno=5, so=so)
+    o.set_state(U, T)
+    o.startup()
+    t0 = time.time()
+    n, _, _ = o.run(nsteps)
+    sec = time.time() - t0
+    return grid[0] * grid[1] * grid[2] * 3.0 * abs(n) / sec / 1e6, "port", sec, 1
+
+
+def cpu_sample_grid(wl):
+    return (128, 64, 64) if wl == "sbi" else (128, 64, 64)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = args.workload
+    grid = cpu_sample_grid(wl)
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 0) and 1):
+        run_cpu_reference(wl, grid, 1, threads)                     # one warm-up pass (page-in of the binary and the tables)
+    val, kind, sec, used = run_cpu_reference(wl, grid, max(args.steps, 1), threads)
+    w = WORKLOADS[wl]
+    sample = "%s, %dx%dx%d inner cells, %d steps (x3 stages), one process, %d OpenMP threads" % (w["ref"] if kind == "reference" else "oracle port", grid[0], grid[1], grid[2], args.steps, used)
+    line = {"impl": "reference", "metric": "cell-updates/sec (Mcell*stage/s)", "value": val, "unit": "Mcell*stage/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": w["desc"] + "; CPU sample " + "x".join(map(str, grid)) + " (the reference cannot allocate 512^3: int cellbytes, 157 GB)",
+                       "grid_per_gpu": list(grid), "flush": "n/a"},
+            "cpu_baseline": {"value": val, "unit": "Mcell*stage/s", "cores": used, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Mcell*stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sbi", choices=sorted(WORKLOADS))
+    ap.add_argument("--grid", default=None, help="nx,ny,nz inner cells per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--fp", type=int, default=0, help="0 strict (parity mode, default), 1 FMA contraction in the sweeps")
+    ap.add_argument("--weno", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from xfluids_b200 import capi, host
+    from xfluids_b200.slab import SlabStepper
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- xfluids_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    w = WORKLOADS[args.workload]
+    grid = tuple(int(x) for x in args.grid.split(",")) if args.grid else w["grid"]
+    cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=LLF", "-fp=%d" % args.fp]
+    if world > 1:
+        cli += ["-mpi=1,1,%d" % world, "-mpi-s=weak"]
+    setup = host.Setup(os.path.join(REPO, "settings", w["json"]), cli, rank=rank, nranks=world)
+    E = setup.Emax
+    ncells = setup.ncells
+    inner = setup.block.X_inner * setup.block.Y_inner * setup.block.Z_inner
+    L = capi.Lib.get()
+
+    # ---- initial condition written straight into pinned host memory (the e2e leg's host buffer) ----
+    nbytes = ncells * E * 8
+    hptr = L.dll.xf_host_alloc_pinned(nbytes)
+    if not hptr:
+        raise SystemExit("cannot pin %d bytes of host memory" % nbytes)
+    hU = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(ncells * E,))
+    t0 = time.time()
+    _, hT = setup.initial_condition(U=hU)
+    t_ic = time.time() - t0
+
+    eng = capi.Engine(setup.block, setup.thermal, setup.scheme, device=local, keepalive=(setup,))
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        eng.upload(eng.U, hU)
+        eng.upload(eng.U1, hU)
+        eng.set_scalar("T", hT)
+        del hT
+        stepper = SlabStepper(eng, setup.bc, rank, world, dev)
+        stepper.startup()
+
+        def run_steps(n):
+            if world == 1:
+                done, _, err = eng.run(setup.bc, n)          # CUDA-graph replay, device-resident dt
+                assert done == n and err == 0, (done, err)
+            else:
+                stepper.steps(n)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        run_steps(max(args.warmup, 3))
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = eng.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(args.steps)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = eng.launches() - l0
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        assert not stepper.any_error(), "numerical guard fired during the timed region"
+        value = inner * world * 3.0 * args.steps / (ms * 1e-3) / 1e6
+
+        # ---- end to end through host buffers: upload AoS U, one step, download AoS U; every step ----
+        e2e = None
+        ke = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 5)
+        if ke > 0 and world == 1:
+            eng.step_host(hptr, setup.bc, 1)                 # warm-up (staging buffer allocation)
+            barrier()
+            e0.record(stream)
+            for _ in range(ke):
+                done, err = eng.step_host(hptr, setup.bc, 1)
+                assert done == 1 and err == 0
+            e1.record(stream)
+            barrier()
+            mse = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            mse = float(mse.item())
+            e2e = {"value": inner * world * 3.0 * ke / (mse * 1e-3) / 1e6, "unit": "Mcell*stage/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                   "steps": ke, "ms_per_step": mse / ke, "api": "xf_step_host (pinned AoS U up, 1 step, AoS U down)"}
+        elif ke > 0:
+            # N > 1: per rank, upload -> K_e steps through the slab stepper -> download, all inside the timed region
+            barrier()
+            e0.record(stream)
+            for _ in range(ke):
+                eng.upload(eng.U, hU)
+                stepper.step()
+                L.check(L.dll.xf_download_aos(eng.ctx, eng.U, hptr))
+            e1.record(stream)
+            barrier()
+            mse = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(mse, op=dist.ReduceOp.MAX)
+            mse = float(mse.item())
+            e2e = {"value": inner * world * 3.0 * ke / (mse * 1e-3) / 1e6, "unit": "Mcell*stage/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+                   "steps": ke, "ms_per_step": mse / ke, "api": "xf_upload_aos + slab step (halo over NCCL) + xf_download_aos per rank"}
+
+        # ---- per-kernel device times of eager steps (CUDA events on the launching stream) ----
+        prof = None
+        if rank == 0 and world == 1 and args.profile_steps > 0:
+            acc = {}
+            for _ in range(args.profile_steps):
+                p = eng.profile_step(setup.bc)
+                for k, v in p.items():
+                    acc[k] = acc.get(k, 0.0) + v / args.profile_steps
+            prof = acc
+    roof = None
+    if prof:
+        dfma, copy = capi.measure_peaks(local)
+        dims = [d for d, on in zip(("sweep_x", "sweep_y", "sweep_z"), (setup.block.DimX, setup.block.DimY, setup.block.DimZ)) if on]
+        top = max(dims, key=lambda k: prof[k])
+        ax = {"sweep_x": 0, "sweep_y": 1, "sweep_z": 2}[top]
+        n_in = [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner]
+        faces = 1
+        for a in range(3):
+            faces *= n_in[a] + 1 if a == ax else n_in[a]
+        fl = sweep_flops_per_face(E, setup.num_species, setup.cop, args.weno) * faces      # per launch
+        t_launch = prof[top] / 3.0 * 1e-3                                                  # 3 launches (stages) per step
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+        roof = {"bound": "fp64", "kernel": "k_sweep<%s>" % top[-1], "achieved": fl / t_launch / 1e12, "peak": dfma, "unit": "TFLOP/s",
+                "frac": fl / t_launch / 1e12 / dfma if dfma else None, "traffic": None,
+                "peak_source": "FP64 FMA rate measured live by xf_measure_peaks on this device (MEASURED_PEAKS.json holds no FP64 figure; nominal 37)",
+                "hbm_view": {"achieved_gbs": sweep_bytes_per_cell(E) * inner / t_launch / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650", "copy_gbs_live": copy},
+                "ms_per_launch": t_launch * 1e3, "flops_per_face": sweep_flops_per_face(E, setup.num_species, setup.cop, args.weno),
+                "step_breakdown_ms": prof}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        g = cpu_sample_grid(args.workload)
+        threads = os.cpu_count() or 1
+        val, kind, sec, used = run_cpu_reference(args.workload, g, 5, threads)
+        cpu = {"value": val, "unit": "Mcell*stage/s", "cores": used, "kind": kind,
+               "sample": "%s: %dx%dx%d inner cells, 5 steps (15 stages), %.1f s, %d OpenMP threads" % (w["ref"] if kind == "reference" else "oracle port", g[0], g[1], g[2], sec, used)}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/sec (Mcell*stage/s)", "value": value, "unit": "Mcell*stage/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "grid_per_gpu": list(grid), "emax": E, "weno": args.weno, "flux_splitting": "LLF",
+                           "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
+                           "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
+                           "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % (eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9),
+                           "ic_seconds_host": round(t_ic, 2)},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    L.dll.xf_host_free_pinned(hptr)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,6 +144,14 @@ int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nstep
 void *xf_host_alloc_pinned(size_t bytes);
 void xf_host_free_pinned(void *p);
 
+/* ---- measurement support (bench.py): no reference counterpart; the reference's wall-clock timers are
+ *      ConVenction_block.hpp:592-614 / UpdateStates_block.cpp:186-190 ------------------------------------------ */
+/* one eager time step with CUDA events between the kernels of every stage.  ms[0] dt, [1] boundary fill, [2] primitive
+ * recovery, [3..5] sweep x/y/z, [6] flux divergence + RK update (each summed over the 3 stages), [7] whole step. */
+int xf_profile_step(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const int bc[6], double t_end, float ms[8]);
+/* roofline denominators measured on `device`: FP64 FMA rate (TFLOP/s, FMA = 2 flop), copy bandwidth (GB/s, read+write) */
+int xf_measure_peaks(int device, double *dfma_tflops, double *copy_gbs);
+
 /* kernel launch counter (bench.py "gpu_launches") */
 long long xf_launch_count(const xf_ctx *ctx);
 

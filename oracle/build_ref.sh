@@ -47,7 +47,7 @@ INCS=(-I"$HERE/shim" -I"$REF/runtime.dat/$MIX" -I"$REF/$SDIR"
       -I"$REF/src/solver_GetDt" -I"$REF/src/solver_Reaction")
 
 if [ "$MODE" = parity ]; then OPT=(-O2 -ffp-contract=off)
-else OPT=(-O3 -march=native -fopenmp); fi
+else OPT=(-O3 -march=x86-64-v3 -fopenmp); fi   # x86-64-v3 (AVX2+FMA): the binary travels to the GPU box, whose CPU may differ
 CXXFLAGS=(-std=c++17 -fpermissive -w -U_FORTIFY_SOURCE -D_FORTIFY_SOURCE=0 "${OPT[@]}")
 
 SRCS=("$REF"/src/Fluids.cpp "$REF"/src/XFLUIDS.cpp "$REF"/src/read_ini/src/*.cpp

@@ -74,6 +74,8 @@ _PROTOS = {
     "xf_host_alloc_pinned": (_P, [C.c_size_t]),
     "xf_host_free_pinned": (None, [_P]),
     "xf_launch_count": (C.c_longlong, [_P]),
+    "xf_profile_step": (C.c_int, [_P, _P, _P, _P, _BC, C.c_double, C.c_float * 8]),
+    "xf_measure_peaks": (C.c_int, [C.c_int, _DP, _DP]),
 }
 
 EXPORTED_SYMBOLS = sorted(_PROTOS)
@@ -108,6 +110,14 @@ class Lib:
 
 def _dptr(a):
     return a.ctypes.data_as(_P)
+
+
+def measure_peaks(device=0):
+    """(FP64 FMA TFLOP/s, copy GB/s) measured on the device by the library's micro-benchmarks."""
+    L = Lib.get()
+    a, b = C.c_double(), C.c_double()
+    L.check(L.dll.xf_measure_peaks(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 class Engine:
@@ -212,6 +222,22 @@ class Engine:
         f = (C.c_int * 4)()
         self.L.check(self.L.dll.xf_error_flags(self.ctx, f))
         return list(f)
+
+    def profile_step(self, bc, t_end=1e300):
+        """One eager step with per-kernel CUDA-event timing: dict of ms (summed over the 3 stages)."""
+        ms = (C.c_float * 8)()
+        self.L.check(self.L.dll.xf_profile_step(self.ctx, self.U, self.U1, self.LU, _BC(*bc), t_end, ms))
+        return dict(zip(("dt", "bc", "prim", "sweep_x", "sweep_y", "sweep_z", "lu_rk", "step"), [float(x) for x in ms]))
+
+    def set_stream(self, cuda_stream):
+        self.L.check(self.L.dll.xf_set_stream(self.ctx, _P(cuda_stream)))
+
+    def step_host(self, h_ptr, bc, nsteps, t_end=1e300):
+        """xf_step_host: upload AoS U from (pinned) host memory, run nsteps, download AoS U into the same buffer."""
+        done, err = C.c_int(), C.c_int()
+        rc = self.L.dll.xf_step_host(self.ctx, _P(h_ptr), _BC(*bc), nsteps, t_end, self.U, self.U1, self.LU, C.byref(done), C.byref(err))
+        self.L.check(rc, allow_numeric=True)
+        return done.value, err.value
 
     def launches(self):
         return self.L.dll.xf_launch_count(self.ctx)

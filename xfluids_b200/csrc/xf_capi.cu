@@ -90,6 +90,27 @@ static int dmalloc(xf_ctx *c, double **p, size_t n)
 	return 0;
 }
 
+
+// ---- roofline denominators measured on the device the bench runs on (bench.py "roofline.peak") ----------------
+// FP64: 8 independent DFMA chains per thread, 1024 threads/SM-slot, long enough to hide launch overhead.
+__global__ void __launch_bounds__(256) k_peak_dfma(double *out, int iters, double a, double b)
+{
+	double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+	for (int i = 0; i < iters; i++)
+	{
+		x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+		x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+	}
+	const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+	if (r == 123.456)
+		out[0] = r;
+}
+__global__ void __launch_bounds__(256) k_peak_copy(const double2 *__restrict__ in, double2 *__restrict__ out, size_t n)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		out[i] = in[i];
+}
+
 extern "C"
 {
 	const char *xf_last_error(void) { return g_err.c_str(); }
@@ -355,7 +376,7 @@ extern "C"
 	}
 	int xf_get_lu(xf_ctx *c, const double *U, double *LU)
 	{
-		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches, 7));
 		KL(c->t->lu(c->d, c->E, LU, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -419,7 +440,7 @@ extern "C"
 		// by the last UpdateStates) -> gather the maxima there
 		if ((rc = update_states(c, UI, flag == 3)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 7));
 		// flux divergence + NaN guard + RK update in one kernel; LU stays in registers
 		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
 		c->launches++;
@@ -522,6 +543,113 @@ extern "C"
 		if (error)
 			*error = err;
 		return err ? XF_ERR_NUMERIC : XF_OK;
+	}
+
+	// ---- per-kernel timing of one eager step (bench.py roofline; CUDA events on the launching stream) ----
+	// ms[0] dt, ms[1] boundary fill, ms[2] primitive recovery, ms[3..5] sweep x/y/z, ms[6] divergence + RK update,
+	// each summed over the three stages of one time step; ms[7] = whole step.
+	int xf_profile_step(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], double t_end, float ms[8])
+	{
+		CU(cudaSetDevice(c->device));
+		const int NE = 1 + 3 * 6 + 1;
+		cudaEvent_t ev[NE];
+		for (int i = 0; i < NE; i++)
+			CU(cudaEventCreate(&ev[i]));
+		int e = 0, rc;
+		CU(cudaEventRecord(ev[e++], c->stream));
+		if ((rc = xf_dt_device(c, t_end)))
+			return rc;
+		for (int flag = 1; flag <= 3; flag++)
+		{
+			double *UI = flag == 1 ? U : U1;
+			CU(cudaEventRecord(ev[e++], c->stream));
+			if ((rc = xf_boundary(c, UI, bc)))
+				return rc;
+			CU(cudaEventRecord(ev[e++], c->stream));
+			if ((rc = update_states(c, UI, flag == 3)))
+				return rc;
+			for (int dir = 0; dir < 3; dir++)
+			{
+				CU(cudaEventRecord(ev[e++], c->stream));
+				KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 1 << dir));
+			}
+			CU(cudaEventRecord(ev[e++], c->stream));
+			KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+			c->launches++;
+		}
+		CU(cudaEventRecord(ev[e++], c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < 8; i++)
+			ms[i] = 0.f;
+		float t;
+		CU(cudaEventElapsedTime(&t, ev[0], ev[1]));
+		ms[0] = t;
+		for (int st = 0; st < 3; st++)
+			for (int q = 0; q < 6; q++)
+			{
+				CU(cudaEventElapsedTime(&t, ev[1 + st * 6 + q], ev[2 + st * 6 + q]));
+				ms[1 + q] += t;
+			}
+		CU(cudaEventElapsedTime(&t, ev[0], ev[NE - 1]));
+		ms[7] = t;
+		for (int i = 0; i < NE; i++)
+			cudaEventDestroy(ev[i]);
+		return XF_OK;
+	}
+
+	// FP64 FMA rate (TFLOP/s, FMA = 2 flop) and device copy bandwidth (GB/s, read + write) of `device`, best of 5.
+	int xf_measure_peaks(int device, double *dfma_tflops, double *copy_gbs)
+	{
+		CU(cudaSetDevice(device));
+		cudaDeviceProp pr;
+		CU(cudaGetDeviceProperties(&pr, device));
+		cudaEvent_t a, b;
+		CU(cudaEventCreate(&a));
+		CU(cudaEventCreate(&b));
+		double *out = nullptr;
+		CU(cudaMalloc((void **)&out, 64));
+		const int iters = 1 << 14, blocks = pr.multiProcessorCount * 8;
+		double best = 0;
+		for (int rep = 0; rep < 6; rep++)
+		{
+			CU(cudaEventRecord(a, 0));
+			k_peak_dfma<<<blocks, 256>>>(out, iters, 0.999999, 1e-7);
+			CU(cudaEventRecord(b, 0));
+			CU(cudaEventSynchronize(b));
+			float ms;
+			CU(cudaEventElapsedTime(&ms, a, b));
+			const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+			if (rep && tf > best)
+				best = tf;
+		}
+		if (dfma_tflops)
+			*dfma_tflops = best;
+		if (copy_gbs)
+		{
+			const size_t n = (size_t)1 << 27; // 2 GiB per buffer as double2
+			double2 *p = nullptr, *q = nullptr;
+			CU(cudaMalloc((void **)&p, n * sizeof(double2)));
+			CU(cudaMalloc((void **)&q, n * sizeof(double2)));
+			CU(cudaMemset(p, 0, n * sizeof(double2)));
+			double bw = 0;
+			for (int rep = 0; rep < 6; rep++)
+			{
+				CU(cudaEventRecord(a, 0));
+				k_peak_copy<<<pr.multiProcessorCount * 16, 256>>>(p, q, n);
+				CU(cudaEventRecord(b, 0));
+				CU(cudaEventSynchronize(b));
+				float ms;
+				CU(cudaEventElapsedTime(&ms, a, b));
+				const double g = 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9;
+				if (rep && g > bw)
+					bw = g;
+			}
+			*copy_gbs = bw;
+			cudaFree(p), cudaFree(q);
+		}
+		cudaFree(out);
+		cudaEventDestroy(a), cudaEventDestroy(b);
+		return XF_OK;
 	}
 
 	// ---- halo -----------------------------------------------------------------------------------

@@ -547,8 +547,8 @@ template <int E, bool TO_SOA>
 __global__ void __launch_bounds__(128) k_layout(XfDev d, double *__restrict__ soa, double *__restrict__ aos)
 {
 	__shared__ double tile[128 * E];
-	const long long row = blockIdx.y;                 // k*Ymax + j
-	const int i0 = blockIdx.x * 128;
+	const long long row = blockIdx.x;                 // k*Ymax + j  (grid.x: up to 2^31-1 rows)
+	const int i0 = blockIdx.y * 128;
 	const int ni = min(128, d.Xmax - i0);
 	const long long abase = (row * d.Xmax + i0) * E;  // AoS doubles
 	const long long sbase = row * d.Xp + i0;
@@ -654,20 +654,21 @@ static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
 	return 0;
 }
 template <class C>
-static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches)
+static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask)
 {
 	int rc = 0;
+	const bool dx = d.DimX && (dirmask & 1), dy = d.DimY && (dirmask & 2), dz = d.DimZ && (dirmask & 4);
 	if (d.weno == 7)
 	{
-		if (d.DimX) rc |= sweep_t<C, 0, 7>(d, U, s), ++*launches;
-		if (d.DimY) rc |= sweep_t<C, 1, 7>(d, U, s), ++*launches;
-		if (d.DimZ) rc |= sweep_t<C, 2, 7>(d, U, s), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s), ++*launches;
 	}
 	else
 	{
-		if (d.DimX) rc |= sweep_t<C, 0, 5>(d, U, s), ++*launches;
-		if (d.DimY) rc |= sweep_t<C, 1, 5>(d, U, s), ++*launches;
-		if (d.DimZ) rc |= sweep_t<C, 2, 5>(d, U, s), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s), ++*launches;
 	}
 	return rc;
 }
@@ -695,9 +696,9 @@ int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, 
 {
 	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s));
 }
-int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches)
+int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask)
 {
-	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches));
+	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask));
 }
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 int launch_lu(const XfDev &d, int E_, double *LU, cudaStream_t s)
@@ -767,7 +768,7 @@ int launch_dt_final(const XfDev &d, double t_end, cudaStream_t s)
 }
 int launch_layout(const XfDev &d, int E_, double *soa, double *aos, int to_soa, cudaStream_t s)
 {
-	dim3 g((d.Xmax + 127) / 128, (unsigned)((long long)d.Ymax * d.Zmax));
+	dim3 g((unsigned)((long long)d.Ymax * d.Zmax), (d.Xmax + 127) / 128);
 	if (to_soa)
 	{
 		XF_DISPATCH_E(E_, k_layout<E, true><<<g, 128, 0, s>>>(d, soa, aos));

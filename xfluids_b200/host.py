@@ -92,9 +92,12 @@ class Setup:
         self.H.dll.xfh_setup_ini(self.h, v)
         return list(v)
 
-    def initial_condition(self):
-        """InitializeFluidStates on the host: returns (U_aos [ncells*Emax], T [ncells])."""
-        U, T = np.empty(self.ncells * self.Emax), np.empty(self.ncells)
+    def initial_condition(self, U=None, T=None):
+        """InitializeFluidStates on the host: returns (U_aos [ncells*Emax], T [ncells]); U / T may be caller-provided
+        (e.g. a view of pinned memory) so that large blocks are written in place."""
+        U = np.empty(self.ncells * self.Emax) if U is None else U
+        T = np.empty(self.ncells) if T is None else T
+        assert U.size == self.ncells * self.Emax and T.size == self.ncells and U.dtype == np.float64 and T.dtype == np.float64
         rc = self.H.dll.xfh_initial_condition(self.h, U.ctypes.data_as(_P), T.ctypes.data_as(_P))
         if rc:
             raise XfError("unknown or inconsistent sample/mixture (rc %d)" % rc)

@@ -1,0 +1,115 @@
+"""z-slab decomposition across the GPUs of one box: the replacement for the reference's MpiTrans (src/mpiPacks/mpiPacks.cpp:3-75,
+357-505) and the MPI calls inside FluidBoundaryCondition / GetFluidDt.
+
+One process per GPU (torch.distributed, backend nccl; gloo in the CPU tests).  Rank r owns Z_inner planes; its z faces carry
+BC_COPY (99) towards a neighbour rank and the physical boundary condition on the outside (mpiPacks.cpp:44-72; the host Setup
+computes that list).  Per RK stage, after the local ghost fill in x and y:
+
+    pack  the Bwidth_Z innermost planes next to each internal face   (FluidMpiCopyKernelZ pack, BCs_kernels.hpp:304-324)
+    send  them to that neighbour / receive the neighbour's planes     (MPI_Sendrecv, mpiPacks.cpp:486-489 -> NCCL send/recv)
+    unpack into the ghost planes of that face                         (FluidMpiCopyKernelZ unpack)
+
+and once per step the three directional dt maxima are MAX-reduced over the ranks (Fluids.cpp:902-913; max is exact, so every
+rank derives the same dt bit for bit).  This module holds the transport-independent part; the device kernels are
+xf_halo_pack / xf_halo_unpack of the C ABI."""
+import torch
+import torch.distributed as dist
+
+BC_COPY = 99
+
+
+class HaloExchanger:
+    """Neighbour exchange of packed z-halo buffers + the scalar reductions of one time step."""
+
+    def __init__(self, rank, world, bc, periodic_z=False, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        # internal faces are the ones the host Setup marked BC_COPY (face 4 = zmin, 5 = zmax)
+        self.lo = (rank - 1) % world if bc[4] == BC_COPY else None
+        self.hi = (rank + 1) % world if bc[5] == BC_COPY else None
+        if not periodic_z:
+            assert (self.lo is None) == (rank == 0) or world == 1
+            assert (self.hi is None) == (rank == world - 1) or world == 1
+
+    def exchange(self, send_lo, send_hi, recv_lo, recv_hi):
+        """send_lo: my inner planes next to zmin -> neighbour rank-1 (lands in ITS zmax ghosts = its recv_hi);
+        send_hi: my inner planes next to zmax -> neighbour rank+1 (its recv_lo).  Returns the outstanding requests."""
+        ops = []
+        if self.hi is not None:
+            ops.append(dist.P2POp(dist.isend, send_hi, self.hi, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self.hi, group=self.group))
+        if self.lo is not None:
+            ops.append(dist.P2POp(dist.isend, send_lo, self.lo, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self.lo, group=self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def allreduce_max(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+class _DevPtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap library-owned memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def wrap_device(ptr, n, dtype=torch.float64, device=None):
+    ts = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DevPtr(ptr, (n,), ts), device=device)
+
+
+class SlabStepper:
+    """The time loop of one rank of a z-slab run: XFLUIDS::Evolution's inner loop (src/XFLUIDS.cpp:172-294) with the halo exchange
+    where FluidBoundaryCondition has its MPI exchange and the dt MAX-reduction where GetFluidDt has its allreduce.  Everything
+    is enqueued on the engine's stream; nothing synchronises with the host inside a step."""
+
+    def __init__(self, eng, bc, rank, world, device):
+        self.eng, self.bc, self.rank, self.world = eng, list(bc), rank, world
+        self.hx = HaloExchanger(rank, world, self.bc)
+        L = eng.L.dll
+        n = L.xf_halo_doubles(eng.ctx)
+        self.buf = {k: torch.empty(n, dtype=torch.float64, device=device) for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
+        self.dtmax = wrap_device(L.xf_device_dtmax(eng.ctx), 3, torch.float64, device)
+        self.errors = wrap_device(L.xf_device_errors(eng.ctx), 4, torch.int32, device)
+
+    def halo(self, field):
+        """z exchange of `field` (a device pointer of the engine): pack -> send/recv -> unpack, on the current stream."""
+        e, L, b = self.eng, self.eng.L, self.buf
+        if self.hx.lo is not None:
+            L.check(L.dll.xf_halo_pack(e.ctx, field, 4, b["send_lo"].data_ptr()))
+        if self.hx.hi is not None:
+            L.check(L.dll.xf_halo_pack(e.ctx, field, 5, b["send_hi"].data_ptr()))
+        for r in self.hx.exchange(b["send_lo"], b["send_hi"], b["recv_lo"], b["recv_hi"]):
+            r.wait()
+        if self.hx.lo is not None:
+            L.check(L.dll.xf_halo_unpack(e.ctx, field, 4, b["recv_lo"].data_ptr()))
+        if self.hx.hi is not None:
+            L.check(L.dll.xf_halo_unpack(e.ctx, field, 5, b["recv_hi"].data_ptr()))
+
+    def startup(self):
+        """main.cpp:44-48: BoundaryCondition + UpdateStates on the initial U."""
+        e = self.eng
+        e.boundary(e.U, self.bc)
+        self.halo(e.U)
+        assert e.update_states(e.U) == 0
+
+    def step(self, t_end=1e300):
+        e = self.eng
+        self.hx.allreduce_max(self.dtmax)       # Fluids.cpp:902-913
+        e.dt_device(t_end)                      # XFLUIDS.cpp:196-199
+        for flag in (1, 2, 3):                  # XFLUIDS.cpp:441-525
+            UI = e.U if flag == 1 else e.U1
+            e.boundary(UI, self.bc)
+            self.halo(UI)
+            e.rk_stage(None, flag)
+
+    def steps(self, n, t_end=1e300):
+        for _ in range(n):
+            self.step(t_end)
+
+    def any_error(self):
+        f = self.errors.clone()
+        self.hx.allreduce_max(f)
+        return bool(f[:3].any().item())
