@@ -189,6 +189,15 @@ extern "C"
 		double *errp = nullptr;
 		rc |= dmalloc(c, &errp, 2);
 		d.err = reinterpret_cast<int *>(errp);
+		if (c->cop)
+		{ // hard-cell list of the two-pass primitive recovery: one 32-bit index per cell at most, + the counter
+			if (N >= (size_t)0xffffffffu)
+				return fail(XF_ERR_ARG, "block too large for 32-bit cell indices");
+			double *hp = nullptr;
+			rc |= dmalloc(c, &hp, N / 2 + 2);
+			d.hard_count = reinterpret_cast<unsigned *>(hp);
+			d.hard_ids = d.hard_count + 2;
+		}
 		if (rc)
 		{
 			xf_destroy(c);
@@ -342,8 +351,7 @@ extern "C"
 		}
 		if (c->sc.artificial_type == 3 && c->sc.weno_order != 7)
 			flags |= 2; // GLF running maxima; for SCHEME_ORDER 7 eigen_local == 0 and the maxima stay 0
-		KL(c->t->prim(c->d, c->th, c->ns, c->cop, U, flags, c->stream));
-		c->launches++;
+		KL(c->t->prim(c->d, c->th, c->ns, c->cop, U, flags, c->stream, &c->launches));
 		c->lastUI = U;
 		return XF_OK;
 	}

@@ -41,124 +41,120 @@ __device__ __forceinline__ bool xf_bad(double x) { return (x < 0) || isnan(x) ||
 // k_prim: Updaterhoyi + UpdateFuidStatesKernel (Update_kernels.hpp:5-48, Update_device.hpp:7-54) over ALL cells
 // incl. ghosts, guards (Estimate_kernels.hpp) on inner cells, and the per-cell halves of ReconstructSoundSpeed.
 // flags: bit0 gather dt maxima, bit1 gather GLF maxima
+//
+// The Newton iteration for T has a data-dependent trip count (1-3 in smooth flow, 20-25 at shock fronts, the
+// 100-iteration cap at fresh discontinuities), so a single pass leaves most lanes of every warp that
+// touches a front idle (ncu: 8.5 of 32 lanes active on average).  Two passes instead, same iteration sequence per cell:
+//   k_prim       every cell, at most XF_NEWTON_FAST iterations; cells that have not met the stop criterion park their
+//                current T / iteration count and append their index to a device list
+//   k_prim_hard  one thread per list entry continues the same iteration to the stop criterion or the cap
+// Both end in the same epilogue.
 // ---------------------------------------------------------------------------------------------
+constexpr int XF_NEWTON_FAST = 3;
+
 template <class C>
-__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags)
+struct PrimCell
 {
-	const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int i = int(lin % d.Xp);
-	const long long row = lin / d.Xp;
-	const bool active = lin < d.N && i < d.Xmax;
-	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-	if (active)
+	double rho, rho1, U1, U2, U3, U4, u, v, w, q2, tme, R, Wm;
+	double yi[C::NS];
+};
+
+// one limited Newton step of get_T (Mixing_device.h:171-193); returns true when the stop criterion is met
+template <class C>
+XF_DEV bool xf_newton_step(const XfThermo &th, const double *yi, double e, double R, double &T)
+{
+	double hi[C::NS];
+	xf_species_h<C>(th, T, hi);
+	double h = 0.0;
+#pragma unroll
+	for (int n = 0; n < C::NS; n++)
+		h += hi[n] * yi[n];
+	const double Cp = xf_mix_cp<C>(th, yi, T);
+	const double func_T = h - R * T - e;
+	const double dfunc_T = Cp - R;
+	double df = xf_min(func_T / (dfunc_T + 1.0e-30), 1e-3 * T);
+	df = xf_max(df, -1e-2 * T);
+	T = T - df;
+	return fabs(df) <= 1.0e-6;
+}
+
+template <class C>
+XF_DEV void prim_epilogue(const XfDev &d, const XfThermo &th, long long id, bool inner, const PrimCell<C> &pc, double T, int flags,
+						  double *dtm, double *glf)
+{
+	constexpr int NS = C::NS, NC = C::NC;
+	const double rho = pc.rho, rho1 = pc.rho1, u = pc.u, v = pc.v, w = pc.w, q2 = pc.q2;
+	double p, gamma;
+	if constexpr (C::COP)
 	{
-		const long long id = lin;
-		const int j = int(row % d.Ymax), k = int(row / d.Ymax);
-		const bool inner = i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
-		constexpr int NS = C::NS, NC = C::NC;
-		const double rho = U[id];
-		const double rho1 = 1.0 / rho;
-		double yi[NS];
-		if constexpr (C::COP)
+		const double R = pc.R, Wm = pc.Wm;
+		const double *yi = pc.yi;
+		p = rho * R * T;
+		const double Cp = xf_mix_cp<C>(th, yi, T);
+		// 4-argument get_CopGamma (Mixing_device.h:114-126)
+		const double CopW = 1.0 / Wm;
+		const double g4 = Cp / (Cp - th.Ru / CopW);
+		gamma = (g4 > 1.0) ? g4 : -1.0;
+		const double H = (pc.U4 + p) * rho1;
+		// per-cell pieces of ReconstructSoundSpeed (Utils_device.hpp:102-131)
+		double hi[NS];
+		xf_species_h<C>(th, T, hi);
+		const double Cv = Cp - th.Ru * Wm;
+		const double g3 = Cp / Cv; // 3-argument get_CopGamma
+		const double prho = p / rho;
+		const double e_l = H - 0.5 * q2 - prho;
+		const double RN = th.Ri[NC];
+		const double RNT = RN * T;
+		d.dpdrho[id] = (g3 - 1.0) * (0.5 * q2 - hi[NC] + Cp * RNT / R);
+#pragma unroll
+		for (int n = 0; n < NC; n++)
 		{
-			if (d.ghost)
-			{ // GhostSpecies: renormalise and write back into U (Update_device.hpp:15-22)
-				yi[NC] = 0.0;
-				double sum_yi = 0.0;
-#pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] = U[(5 + ii) * d.N + id] * rho1, sum_yi += yi[ii];
-				sum_yi = 1.0 / sum_yi;
-#pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] *= sum_yi, U[(5 + ii) * d.N + id] = rho * yi[ii];
-			}
-			else
-			{
-				yi[NC] = 1.0;
-#pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] = U[(5 + ii) * d.N + id] * rho1, yi[NC] += -yi[ii];
-			}
+			const double hN_minus_hi = -hi[n] + hi[NC];
+			const double Ri_minus_RN = (th.Ri[n] - RN);
+			d.dpdrhoi[n * d.N + id] = (g3 - 1.0) * (hN_minus_hi + Cp * Ri_minus_RN * T / R);
 		}
-		const double U1 = U[1 * d.N + id], U2 = U[2 * d.N + id], U3 = U[3 * d.N + id], U4 = U[4 * d.N + id];
-		const double u = U1 * rho1, v = U2 * rho1, w = U3 * rho1;
-		const double q2 = u * u + v * v + w * w;
-		const double tme = U4 * rho1 - 0.5 * q2;
-		double p, gamma, T = 0.0;
+		d.g3[id] = g3, d.e[id] = e_l, d.prho[id] = prho;
+		d.T[id] = T, d.H[id] = H;
+	}
+	else
+	{
+		gamma = d.gamma0;
+		p = (d.gamma0 - 1.0) * rho * pc.tme;
+		d.H[id] = (pc.U4 + p) * rho1;
+	}
+	const double cc = sqrt(gamma * p * rho1);
+	d.u[id] = u, d.v[id] = v, d.w[id] = w, d.p[id] = p, d.c[id] = cc;
+
+	// guards (flag only): EstimateYiKernel / EstimatePrimitiveVarKernel, inner cells
+	if (inner)
+	{
+		bool e0 = xf_bad(rho);
 		if constexpr (C::COP)
 		{
-			double Wm = 0.0; // sum yi/Wi
 #pragma unroll
 			for (int n = 0; n < NS; n++)
-				Wm += yi[n] * th._Wi[n];
-			const double R = Wm * th.Ru;
-			T = xf_get_T<C>(th, yi, tme, d.T[id], R);
-			p = rho * R * T;
-			const double Cp = xf_mix_cp<C>(th, yi, T);
-			// 4-argument get_CopGamma (Mixing_device.h:114-126)
-			const double CopW = 1.0 / Wm;
-			const double g4 = Cp / (Cp - th.Ru / CopW);
-			gamma = (g4 > 1.0) ? g4 : -1.0;
-			const double H = (U4 + p) * rho1;
-			// per-cell pieces of ReconstructSoundSpeed (Utils_device.hpp:102-131)
-			double hi[NS];
-			xf_species_h<C>(th, T, hi);
-			const double Cv = Cp - th.Ru * Wm;
-			const double g3 = Cp / Cv; // 3-argument get_CopGamma
-			const double prho = p / rho;
-			const double e_l = H - 0.5 * q2 - prho;
-			const double RN = th.Ri[NC];
-			const double RNT = RN * T;
-			d.dpdrho[id] = (g3 - 1.0) * (0.5 * q2 - hi[NC] + Cp * RNT / R);
-#pragma unroll
-			for (int n = 0; n < NC; n++)
-			{
-				const double hN_minus_hi = -hi[n] + hi[NC];
-				const double Ri_minus_RN = (th.Ri[n] - RN);
-				d.dpdrhoi[n * d.N + id] = (g3 - 1.0) * (hN_minus_hi + Cp * Ri_minus_RN * T / R);
-				d.y[n * d.N + id] = yi[n];
-			}
-			d.y[NC * d.N + id] = yi[NC];
-			d.g3[id] = g3, d.e[id] = e_l, d.prho[id] = prho;
-			d.T[id] = T, d.H[id] = H;
+				e0 = e0 || isnan(pc.yi[n]) || isinf(pc.yi[n]);
 		}
-		else
-		{
-			gamma = d.gamma0;
-			p = (d.gamma0 - 1.0) * rho * tme;
-			d.H[id] = (U4 + p) * rho1;
-		}
-		const double cc = sqrt(gamma * p * rho1);
-		d.u[id] = u, d.v[id] = v, d.w[id] = w, d.p[id] = p, d.c[id] = cc;
-
-		// guards (flag only): EstimateYiKernel / EstimatePrimitiveVarKernel, inner cells
-		if (inner)
-		{
-			bool e0 = xf_bad(rho);
-			if constexpr (C::COP)
-			{
-#pragma unroll
-				for (int n = 0; n < NS; n++)
-					e0 = e0 || isnan(yi[n]) || isinf(yi[n]);
-			}
-			if (e0)
-				d.err[0] = 1;
-			if (xf_bad(rho) || xf_bad(p) || (C::COP && xf_bad(T)))
-				d.err[1] = 1;
-		}
-		if (flags & 1)
-		{ // GetDt: hard-coded 1.4, all cells incl. ghosts (GlobalDt_block.hpp:34-66)
-			const double c_local = sqrt(1.4 * p / rho);
-			dtm[0] = fabs(u) + c_local, dtm[1] = fabs(v) + c_local, dtm[2] = fabs(w) + c_local;
-		}
-		if (flags & 2)
-		{ // GetLocalEigen maxima (Eigen_value.hpp:19-28): u_d - c, u_d, u_d + c
-			glf[0] = fabs(u - cc), glf[1] = fabs(u), glf[2] = fabs(u + cc);
-			glf[3] = fabs(v - cc), glf[4] = fabs(v), glf[5] = fabs(v + cc);
-			glf[6] = fabs(w - cc), glf[7] = fabs(w), glf[8] = fabs(w + cc);
-		}
+		if (e0)
+			d.err[0] = 1;
+		if (xf_bad(rho) || xf_bad(p) || (C::COP && xf_bad(T)))
+			d.err[1] = 1;
 	}
+	if (flags & 1)
+	{ // GetDt: hard-coded 1.4, all cells incl. ghosts (GlobalDt_block.hpp:34-66)
+		const double c_local = sqrt(1.4 * p / rho);
+		dtm[0] = fabs(u) + c_local, dtm[1] = fabs(v) + c_local, dtm[2] = fabs(w) + c_local;
+	}
+	if (flags & 2)
+	{ // GetLocalEigen maxima (Eigen_value.hpp:19-28): u_d - c, u_d, u_d + c
+		glf[0] = fabs(u - cc), glf[1] = fabs(u), glf[2] = fabs(u + cc);
+		glf[3] = fabs(v - cc), glf[4] = fabs(v), glf[5] = fabs(v + cc);
+		glf[6] = fabs(w - cc), glf[7] = fabs(w), glf[8] = fabs(w + cc);
+	}
+}
+
+__device__ __forceinline__ void prim_reduce(const XfDev &d, int flags, const double *dtm, const double *glf)
+{
 	if (flags & 1)
 	{
 		if (d.DimX) warp_atomic_max_pos(d.red + XF_RED_DTMAX + 0, dtm[0]);
@@ -171,6 +167,126 @@ __global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__re
 		for (int q = 0; q < 9; q++)
 			if ((q < 3 && d.DimX) || (q >= 3 && q < 6 && d.DimY) || (q >= 6 && d.DimZ))
 				warp_atomic_max_pos(d.red + XF_RED_GLF + q, glf[q]);
+	}
+}
+
+__device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
+{
+	const int i = int(id % d.Xp);
+	const long long row = id / d.Xp;
+	const int j = int(row % d.Ymax), k = int(row / d.Ymax);
+	return i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags)
+{
+	const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool active = lin < d.N && int(lin % d.Xp) < d.Xmax;
+	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (active)
+	{
+		const long long id = lin;
+		constexpr int NS = C::NS, NC = C::NC;
+		PrimCell<C> pc;
+		pc.rho = U[id];
+		pc.rho1 = 1.0 / pc.rho;
+		if constexpr (C::COP)
+		{
+			double *yi = pc.yi;
+			if (d.ghost)
+			{ // GhostSpecies: renormalise and write back into U (Update_device.hpp:15-22)
+				yi[NC] = 0.0;
+				double sum_yi = 0.0;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] = U[(5 + ii) * d.N + id] * pc.rho1, sum_yi += yi[ii];
+				sum_yi = 1.0 / sum_yi;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] *= sum_yi, U[(5 + ii) * d.N + id] = pc.rho * yi[ii];
+			}
+			else
+			{
+				yi[NC] = 1.0;
+#pragma unroll
+				for (int ii = 0; ii < NC; ii++)
+					yi[ii] = U[(5 + ii) * d.N + id] * pc.rho1, yi[NC] += -yi[ii];
+			}
+#pragma unroll
+			for (int n = 0; n < NS; n++)
+				d.y[n * d.N + id] = yi[n];
+		}
+		pc.U1 = U[1 * d.N + id], pc.U2 = U[2 * d.N + id], pc.U3 = U[3 * d.N + id], pc.U4 = U[4 * d.N + id];
+		pc.u = pc.U1 * pc.rho1, pc.v = pc.U2 * pc.rho1, pc.w = pc.U3 * pc.rho1;
+		pc.q2 = pc.u * pc.u + pc.v * pc.v + pc.w * pc.w;
+		pc.tme = pc.U4 * pc.rho1 - 0.5 * pc.q2;
+		double T = 0.0;
+		bool done = true;
+		if constexpr (C::COP)
+		{
+			double Wm = 0.0; // sum yi/Wi
+#pragma unroll
+			for (int n = 0; n < NS; n++)
+				Wm += pc.yi[n] * th._Wi[n];
+			pc.Wm = Wm, pc.R = Wm * th.Ru;
+			T = d.T[id];
+			done = false;
+			for (int it = 1; it <= XF_NEWTON_FAST; it++)
+				if (xf_newton_step<C>(th, pc.yi, pc.tme, pc.R, T))
+				{
+					done = true;
+					break;
+				}
+			if (!done)
+			{ // park: T after XF_NEWTON_FAST steps; k_prim_hard resumes at iteration XF_NEWTON_FAST + 1
+				d.T[id] = T;
+				const unsigned slot = atomicAdd(d.hard_count, 1u);
+				d.hard_ids[slot] = (unsigned)id;
+			}
+		}
+		if (done)
+			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, flags, dtm, glf);
+	}
+	prim_reduce(d, flags, dtm, glf);
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_prim_hard(XfDev d, XfThermo th, const double *__restrict__ U, int flags)
+{
+	constexpr int NS = C::NS;
+	const unsigned count = *d.hard_count;
+	const unsigned stride = gridDim.x * blockDim.x;
+	// warp-uniform trip count: every lane of a warp takes part in the shuffles of prim_reduce
+	for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride)
+	{
+		const unsigned q = base + (threadIdx.x & 31u);
+		double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+		if (q < count)
+		{
+			const long long id = d.hard_ids[q];
+			PrimCell<C> pc;
+			pc.rho = U[id];
+			pc.rho1 = 1.0 / pc.rho;
+#pragma unroll
+			for (int n = 0; n < NS; n++)
+				pc.yi[n] = d.y[n * d.N + id];
+			pc.U1 = U[1 * d.N + id], pc.U2 = U[2 * d.N + id], pc.U3 = U[3 * d.N + id], pc.U4 = U[4 * d.N + id];
+			pc.u = pc.U1 * pc.rho1, pc.v = pc.U2 * pc.rho1, pc.w = pc.U3 * pc.rho1;
+			pc.q2 = pc.u * pc.u + pc.v * pc.v + pc.w * pc.w;
+			pc.tme = pc.U4 * pc.rho1 - 0.5 * pc.q2;
+			double Wm = 0.0;
+#pragma unroll
+			for (int n = 0; n < NS; n++)
+				Wm += pc.yi[n] * th._Wi[n];
+			pc.Wm = Wm, pc.R = Wm * th.Ru;
+			double T = d.T[id];
+			for (int it = XF_NEWTON_FAST + 1; it < 101; it++)
+				if (xf_newton_step<C>(th, pc.yi, pc.tme, pc.R, T))
+					break;
+			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, flags, dtm, glf);
+		}
+		prim_reduce(d, flags, dtm, glf);
 	}
 }
 
@@ -616,11 +732,31 @@ __global__ void __launch_bounds__(256) k_halo(XfDev d, double *__restrict__ U, d
 	} while (0)
 
 template <class C>
-static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s)
+static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches)
 {
 	const long long nb = (d.N + 127) / 128;
+	if constexpr (C::COP)
+	{
+		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
+		if (e != cudaSuccess)
+			return (int)e;
+	}
 	k_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, U, flags);
 	XF_CHECK_LAUNCH();
+	++*launches;
+	if constexpr (C::COP)
+	{
+		static int nsm = 0;
+		if (!nsm)
+		{
+			int dev = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+		}
+		k_prim_hard<C><<<nsm * 8, 128, 0, s>>>(d, th, U, flags);
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
 	return 0;
 }
 
@@ -692,9 +828,9 @@ static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *
 	default: return -1;                                 \
 	}
 
-int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s)
+int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches)
 {
-	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s));
+	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s, launches));
 }
 int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask)
 {

@@ -29,6 +29,7 @@ struct XfDev
 	double *Fw[3];                     // wall fluxes [E][N] per direction
 	double *red;                       // XF_RED_* slots
 	int *err;                          // [4]
+	unsigned *hard_ids, *hard_count;   // cells whose Newton iteration needs more than XF_NEWTON_FAST steps (k_prim -> k_prim_hard)
 };
 
 // NASA-9 tables, re-laid-out per temperature range so that a warp-uniform branch on the range gives
