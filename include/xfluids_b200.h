@@ -138,6 +138,19 @@ size_t xf_halo_doubles(const xf_ctx *ctx);                               /* Emax
 int xf_halo_pack(xf_ctx *ctx, const double *d_UI, int face, double *d_buf);   /* face 4 = zmin inner planes, 5 = zmax */
 int xf_halo_unpack(xf_ctx *ctx, double *d_UI, int face, const double *d_buf); /* into the ghost planes of that face */
 
+int xf_halo_pack_on(xf_ctx *ctx, const double *d_UI, int face, double *d_buf, void *cuda_stream);   /* same, on an explicit stream */
+int xf_halo_unpack_on(xf_ctx *ctx, double *d_UI, int face, const double *d_buf, void *cuda_stream);
+/* One RK stage split around the exchange so that it overlaps with compute (the reference's exchange is blocking and
+ * barrier-fenced, BCs_block.cpp:50-217 / mpiPacks.cpp:405-494):
+ *   xf_boundary -> xf_halo_pack -> [send/recv + xf_halo_unpack_on a second stream]
+ *   xf_stage_interior: primitive recovery of the planes that do not depend on the incoming halo (all but the z ghosts) and
+ *                      the x and y sweeps (they only read inner z planes)
+ *   [wait for the unpack]
+ *   xf_stage_finish:   primitive recovery of the z ghost planes, the z sweep, flux divergence + NaN guard + RK update
+ * Results are bit-identical to xf_rk_stage. */
+int xf_stage_interior(xf_ctx *ctx, double *d_U, double *d_U1, int flag);
+int xf_stage_finish(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
+
 /* ---- host-buffer convenience used for end-to-end timing: upload AoS U, run nsteps, download AoS U ---- */
 int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nsteps, double t_end,
                  double *d_U, double *d_U1, double *d_LU, int *steps_done, int *error);

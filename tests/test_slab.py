@@ -1,0 +1,45 @@
+"""The N > 1 path (z-slab decomposition, halo exchange, dt MAX-reduction).
+
+CPU (-m "not gpu"): world_size-2 and -3 gloo runs of tests/slab_check.py --mode cpu: neighbour bookkeeping of the host Setup
+(-mpi / -mpi-s, BC_COPY faces) and the exchange protocol reproduce the ghost planes of the undecomposed block bit for bit.
+GPU (-m gpu, needs >= 2 devices; run by hand with `gpurun --gpus 2`): two slabs on two GPUs over NCCL, blocking and overlapped
+exchange, against the undecomposed block on one GPU -- bit-exact."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _launch(nproc, args, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "slab_check.py")] + args
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0 and "SLAB_CHECK_OK" in r.stdout, r.stdout[-3000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("world,case,strong", [(2, "sbi", False), (3, "sbi", False), (2, "jet", True)])
+def test_exchange_protocol_gloo(world, case, strong):
+    _launch(world, ["--mode", "cpu", "--case", case] + (["--strong"] if strong else []))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,strong", [("sbi", False), ("jet", True)])
+def test_two_slabs_equal_one_block_bitwise(case, strong):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5"] + (["--strong"] if strong else []))

@@ -70,6 +70,10 @@ _PROTOS = {
     "xf_halo_doubles": (C.c_size_t, [_P]),
     "xf_halo_pack": (C.c_int, [_P, _P, C.c_int, _P]),
     "xf_halo_unpack": (C.c_int, [_P, _P, C.c_int, _P]),
+    "xf_halo_pack_on": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "xf_halo_unpack_on": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "xf_stage_interior": (C.c_int, [_P, _P, _P, C.c_int]),
+    "xf_stage_finish": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_step_host": (C.c_int, [_P, _P, _BC, C.c_int, C.c_double, _P, _P, _P, _IP, _IP]),
     "xf_host_alloc_pinned": (_P, [C.c_size_t]),
     "xf_host_free_pinned": (None, [_P]),
@@ -200,6 +204,12 @@ class Engine:
     def rk_stage(self, bc, flag):
         b = _BC(*bc) if bc is not None else None
         self.L.check(self.L.dll.xf_rk_stage(self.ctx, self.U, self.U1, self.LU, b, flag))
+
+    def stage_interior(self, flag):
+        self.L.check(self.L.dll.xf_stage_interior(self.ctx, self.U, self.U1, flag))
+
+    def stage_finish(self, flag):
+        self.L.check(self.L.dll.xf_stage_finish(self.ctx, self.U, self.U1, self.LU, flag))
 
     def dt_device(self, t_end=1e300):
         self.L.check(self.L.dll.xf_dt_device(self.ctx, t_end))

@@ -341,20 +341,23 @@ extern "C"
 		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches));
 		return XF_OK;
 	}
-	static int update_states(xf_ctx *c, double *U, bool gather_dt)
+	// planes [k0, k1) ; reset_dt: zero the dt maxima first (the first call of a gather)
+	static int update_states_range(xf_ctx *c, double *U, bool gather_dt, bool reset_dt, int k0, int k1)
 	{
 		int flags = 0;
 		if (gather_dt)
 		{
-			CU(cudaMemsetAsync(c->d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
+			if (reset_dt)
+				CU(cudaMemsetAsync(c->d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
 			flags |= 1;
 		}
 		if (c->sc.artificial_type == 3 && c->sc.weno_order != 7)
 			flags |= 2; // GLF running maxima; for SCHEME_ORDER 7 eigen_local == 0 and the maxima stay 0
-		KL(c->t->prim(c->d, c->th, c->ns, c->cop, U, flags, c->stream, &c->launches));
+		KL(c->t->prim(c->d, c->th, c->ns, c->cop, U, flags, c->stream, &c->launches, k0, k1));
 		c->lastUI = U;
 		return XF_OK;
 	}
+	static int update_states(xf_ctx *c, double *U, bool gather_dt) { return update_states_range(c, U, gather_dt, true, 0, c->d.Zmax); }
 	int xf_error_flags(xf_ctx *c, int flags[4])
 	{
 		CU(cudaMemcpyAsync(c->h_err, c->d.err, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -450,6 +453,33 @@ extern "C"
 			return rc;
 		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 7));
 		// flux divergence + NaN guard + RK update in one kernel; LU stays in registers
+		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+		c->launches++;
+		return XF_OK;
+	}
+	// ---- one stage split around the z-halo exchange (multi-GPU overlap; include/xfluids_b200.h) --------------
+	int xf_stage_interior(xf_ctx *c, double *U, double *U1, int flag)
+	{
+		if (flag < 1 || flag > 3 || !c->d.DimZ)
+			return fail(XF_ERR_ARG, "xf_stage_interior: flag 1..3 and an active z dimension");
+		double *UI = flag == 1 ? U : U1;
+		int rc;
+		if ((rc = update_states_range(c, UI, flag == 3, true, c->d.Bz, c->d.Zmax - c->d.Bz)))
+			return rc;
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 3));
+		return XF_OK;
+	}
+	int xf_stage_finish(xf_ctx *c, double *U, double *U1, double *LU, int flag)
+	{
+		if (flag < 1 || flag > 3 || !c->d.DimZ)
+			return fail(XF_ERR_ARG, "xf_stage_finish: flag 1..3 and an active z dimension");
+		double *UI = flag == 1 ? U : U1;
+		int rc;
+		if ((rc = update_states_range(c, UI, flag == 3, false, 0, c->d.Bz)))
+			return rc;
+		if ((rc = update_states_range(c, UI, flag == 3, false, c->d.Zmax - c->d.Bz, c->d.Zmax)))
+			return rc;
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 4));
 		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -662,6 +692,22 @@ extern "C"
 
 	// ---- halo -----------------------------------------------------------------------------------
 	size_t xf_halo_doubles(const xf_ctx *c) { return (size_t)c->E * c->d.Bz * (size_t)c->d.sZ; }
+	int xf_halo_pack_on(xf_ctx *c, const double *U, int face, double *buf, void *stream)
+	{
+		cudaStream_t keep = c->stream;
+		c->stream = (cudaStream_t)stream;
+		const int rc = xf_halo_pack(c, U, face, buf);
+		c->stream = keep;
+		return rc;
+	}
+	int xf_halo_unpack_on(xf_ctx *c, double *U, int face, const double *buf, void *stream)
+	{
+		cudaStream_t keep = c->stream;
+		c->stream = (cudaStream_t)stream;
+		const int rc = xf_halo_unpack(c, U, face, buf);
+		c->stream = keep;
+		return rc;
+	}
 	int xf_halo_pack(xf_ctx *c, const double *U, int face, double *buf)
 	{
 		if (!c->d.DimZ || (face != 4 && face != 5))

@@ -179,10 +179,10 @@ __device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
 }
 
 template <class C>
-__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags)
+__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0, long long lin1)
 {
-	const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = lin < d.N && int(lin % d.Xp) < d.Xmax;
+	const long long lin = lin0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool active = lin < lin1 && int(lin % d.Xp) < d.Xmax;
 	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	if (active)
 	{
@@ -732,16 +732,20 @@ __global__ void __launch_bounds__(256) k_halo(XfDev d, double *__restrict__ U, d
 	} while (0)
 
 template <class C>
-static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches)
+static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1)
 {
-	const long long nb = (d.N + 127) / 128;
+	// z-planes [k0, k1) of the block (all of it: 0, Zmax)
+	const long long lin0 = (long long)k0 * d.sZ, lin1 = (long long)k1 * d.sZ;
+	const long long nb = (lin1 - lin0 + 127) / 128;
+	if (nb <= 0)
+		return 0;
 	if constexpr (C::COP)
 	{
 		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
 		if (e != cudaSuccess)
 			return (int)e;
 	}
-	k_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, U, flags);
+	k_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, U, flags, lin0, lin1);
 	XF_CHECK_LAUNCH();
 	++*launches;
 	if constexpr (C::COP)
@@ -828,9 +832,9 @@ static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *
 	default: return -1;                                 \
 	}
 
-int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches)
+int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1)
 {
-	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s, launches));
+	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s, launches, k0, k1));
 }
 int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask)
 {

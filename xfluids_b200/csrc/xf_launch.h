@@ -6,7 +6,7 @@
 #define XF_DECLARE_LAUNCHERS(NS)                                                                                              \
 	namespace NS                                                                                                              \
 	{                                                                                                                         \
-		int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches); \
+		int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1); \
 		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask); \
 		int launch_lu(const XfDev &d, int E, double *LU, cudaStream_t s);                                                     \
 		int launch_rk(const XfDev &d, int E, double *U, double *U1, const double *LU, double dt, const double *dt_dev,       \

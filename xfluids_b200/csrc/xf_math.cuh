@@ -192,6 +192,35 @@ XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v
 	return W0 * q0 + W1 * q1 + W2 * q2 + W3 * q3;
 }
 
+// Lax-Friedrichs splitting pp = 0.5 (ff + av uf), mm = 0.5 (ff - av uf) and the +/- reconstructions of one
+// characteristic field (Eigen_callback.h:194-208 / 146-163).  Deliberately NOT inlined: the field loop of xf_face_flux is
+// fully unrolled (every field has its own sparse projection), and nine inlined copies of this body push the sweep kernel
+// to ~78 KB of SASS, which showed up in ncu as the top stall reason ("no instruction").
+static __device__ __noinline__ double xf_split_weno5(double av, double u0, double u1, double u2, double u3, double u4, double u5,
+											  double f0, double f1, double f2, double f3, double f4, double f5)
+{
+	// stencil s=0..5 <-> cells i-2..i+3 ; weno5old_GPU(&pp[3],&mm[3]): plus uses i-2..i+2, minus i+3..i-1
+	const double a0 = av * u0, a1 = av * u1, a2 = av * u2, a3 = av * u3, a4 = av * u4, a5 = av * u5;
+	const double p1 = 0.5 * (f0 + a0), p2 = 0.5 * (f1 + a1), p3 = 0.5 * (f2 + a2), p4 = 0.5 * (f3 + a3), p5 = 0.5 * (f4 + a4);
+	const double m1 = 0.5 * (f5 - a5), m2 = 0.5 * (f4 - a4), m3 = 0.5 * (f3 - a3), m4 = 0.5 * (f2 - a2), m5 = 0.5 * (f1 - a1);
+	return (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
+}
+static __device__ __noinline__ double xf_split_weno7(double av, double u0, double u1, double u2, double u3, double u4, double u5, double u6, double u7,
+											  double f0, double f1, double f2, double f3, double f4, double f5, double f6, double f7)
+{
+	const double uf[8] = {u0, u1, u2, u3, u4, u5, u6, u7}, ff[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+	double pp[8], mm[8];
+#pragma unroll
+	for (int s = 0; s < 8; s++)
+	{
+		const double au = av * uf[s];
+		pp[s] = 0.5 * (ff[s] + au);
+		mm[s] = 0.5 * (ff[s] - au);
+	}
+	// weno7_P(&pp[3]): f[-3..3]; weno7_M(&mm[3]): k=1, v1=f[4] ... v7=f[-2]
+	return xf_weno7_body(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6]) + xf_weno7_body(mm[7], mm[6], mm[5], mm[4], mm[3], mm[2], mm[1]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Roe state at a face (MARCO_ROE global_marco.h:26-34, ReconstructSoundSpeed Utils_device.hpp:102-140,
 // SoundSpeedMultiSpecies :42-79, MARCO_NOCOPC2 / MARCO_PREEIGEN Eigen_callback.h:87-106)
@@ -311,6 +340,18 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 	const double un_c = un * R.c1;
 	const double b1 = R.b1, b2 = R.b2, b3 = R.b3, c1 = R.c1;
 
+	// local Lax-Friedrichs wave speeds: max over the stencil of |u_d - c|, |u_d|, |u_d + c| -- the same for every field of a
+	// family, so formed once per face (the reference re-forms it per field; max is exact, the order is kept)
+	double lmax[3] = {0.0, 0.0, 0.0};
+	if (alpha == 2 && WENO != 7)
+	{
+#pragma unroll
+		for (int t = 0; t < 3; t++)
+#pragma unroll
+			for (int s = 0; s < NST; s++)
+				lmax[t] = xf_max(lmax[t], st.lam(s, t));
+	}
+
 	double f[E];
 #pragma unroll
 	for (int n = 0; n < E; n++)
@@ -318,24 +359,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 		// ---- artificial viscosity for this field (Eigen_callback.h:134-145, 188-193) ----
 		const int t = (n == 0) ? 0 : ((n == E - 1) ? 2 : 1);
 		const double ev = (n == 0) ? fabs(un - R.c) : ((n == E - 1) ? fabs(un + R.c) : fabs(un));
-		double av;
-		if (alpha == 1)
-			av = ev;
-		else if (alpha == 2)
-		{
-			if constexpr (WENO == 7)
-				av = ev; // eigen_local == 0 for SCHEME_ORDER 7 (Eigen_value.hpp:29-32): the sign test never fires
-			else
-			{
-				double m = 0.0;
-#pragma unroll
-				for (int s = 0; s < NST; s++)
-					m = xf_max(m, st.lam(s, t));
-				av = m;
-			}
-		}
-		else
-			av = glf[t];
+		// WENO7: eigen_local == 0 for SCHEME_ORDER 7 (Eigen_value.hpp:29-32), the sign test never fires -> LLF == ROE
+		const double av = (alpha == 1 || (alpha == 2 && WENO == 7)) ? ev : ((alpha == 2) ? lmax[t] : glf[t]);
 
 		// ---- project the stencil on row n of L ----
 		double uf[NST], ff[NST];
@@ -432,34 +457,11 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 			}
 		}
 
-		// ---- Lax-Friedrichs splitting + WENO ----
+		// ---- Lax-Friedrichs splitting + WENO (one out-of-line copy: keeps the kernel inside the instruction cache) ----
 		if constexpr (WENO == 7)
-		{
-			double pp[8], mm[8];
-#pragma unroll
-			for (int s = 0; s < 8; s++)
-			{
-				const double au = av * uf[s];
-				pp[s] = 0.5 * (ff[s] + au);
-				mm[s] = 0.5 * (ff[s] - au);
-			}
-			// weno7_P(&pp[3]): f[-3..3]; weno7_M(&mm[3]): k=1, v1=f[4] ... v7=f[-2]
-			f[n] = xf_weno7_body(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6]) +
-				   xf_weno7_body(mm[7], mm[6], mm[5], mm[4], mm[3], mm[2], mm[1]);
-		}
+			f[n] = xf_split_weno7(av, uf[0], uf[1], uf[2], uf[3], uf[4], uf[5], uf[6], uf[7], ff[0], ff[1], ff[2], ff[3], ff[4], ff[5], ff[6], ff[7]);
 		else
-		{
-			// stencil s=0..5 <-> cells i-2..i+3 ; weno5old_GPU(&pp[3],&mm[3]): plus uses i-2..i+2, minus i+3..i-1
-			double au[6];
-#pragma unroll
-			for (int s = 0; s < 6; s++)
-				au[s] = av * uf[s];
-			const double p1 = 0.5 * (ff[0] + au[0]), p2 = 0.5 * (ff[1] + au[1]), p3 = 0.5 * (ff[2] + au[2]),
-						 p4 = 0.5 * (ff[3] + au[3]), p5 = 0.5 * (ff[4] + au[4]);
-			const double m1 = 0.5 * (ff[5] - au[5]), m2 = 0.5 * (ff[4] - au[4]), m3 = 0.5 * (ff[3] - au[3]),
-						 m4 = 0.5 * (ff[2] - au[2]), m5 = 0.5 * (ff[1] - au[1]);
-			f[n] = (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
-		}
+			f[n] = xf_split_weno5(av, uf[0], uf[1], uf[2], uf[3], uf[4], uf[5], ff[0], ff[1], ff[2], ff[3], ff[4], ff[5]);
 		// compiler fence: forbid keeping stencil values loaded for this field alive into the next one
 		// (without it the unrolled field loop is CSE'd into ~2*E*NST live doubles and spills)
 		asm volatile("" ::: "memory");

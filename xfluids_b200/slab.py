@@ -65,8 +65,10 @@ class SlabStepper:
     where FluidBoundaryCondition has its MPI exchange and the dt MAX-reduction where GetFluidDt has its allreduce.  Everything
     is enqueued on the engine's stream; nothing synchronises with the host inside a step."""
 
-    def __init__(self, eng, bc, rank, world, device):
+    def __init__(self, eng, bc, rank, world, device, overlap=True):
         self.eng, self.bc, self.rank, self.world = eng, list(bc), rank, world
+        self.overlap = overlap and world > 1 and eng.block.DimZ
+        self.comm = None
         self.hx = HaloExchanger(rank, world, self.bc)
         L = eng.L.dll
         n = L.xf_halo_doubles(eng.ctx)
@@ -95,15 +97,55 @@ class SlabStepper:
         self.halo(e.U)
         assert e.update_states(e.U) == 0
 
+    # ---- one stage, exchange blocking (reference order: BC + exchange, UpdateStates, GetLU, UpdateU) ----
+    def stage_blocking(self, flag):
+        e = self.eng
+        UI = e.U if flag == 1 else e.U1
+        e.boundary(UI, self.bc)
+        self.halo(UI)
+        e.rk_stage(None, flag)
+
+    # ---- one stage, exchange overlapped with the interior work ----
+    def stage_overlapped(self, flag):
+        """pack on the compute stream (before the primitive recovery rewrites the species of U), then the exchange and the
+        unpack on the communication stream while the compute stream recovers the primitives of all non-ghost planes and runs
+        the x and y sweeps; the z ghost planes' primitives, the z sweep and the update wait for the unpack."""
+        e, L, b = self.eng, self.eng.L, self.buf
+        main = torch.cuda.current_stream()
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=main.device)
+            self.ev_packed = torch.cuda.Event()
+            self.ev_unpacked = torch.cuda.Event()
+        UI = e.U if flag == 1 else e.U1
+        e.boundary(UI, self.bc)
+        if self.hx.lo is not None:
+            L.check(L.dll.xf_halo_pack(e.ctx, UI, 4, b["send_lo"].data_ptr()))
+        if self.hx.hi is not None:
+            L.check(L.dll.xf_halo_pack(e.ctx, UI, 5, b["send_hi"].data_ptr()))
+        self.ev_packed.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_packed)
+            for r in self.hx.exchange(b["send_lo"], b["send_hi"], b["recv_lo"], b["recv_hi"]):
+                r.wait()
+            cs = self.comm.cuda_stream
+            if self.hx.lo is not None:
+                L.check(L.dll.xf_halo_unpack_on(e.ctx, UI, 4, b["recv_lo"].data_ptr(), cs))
+            if self.hx.hi is not None:
+                L.check(L.dll.xf_halo_unpack_on(e.ctx, UI, 5, b["recv_hi"].data_ptr(), cs))
+            self.ev_unpacked.record(self.comm)
+        e.stage_interior(flag)
+        main.wait_event(self.ev_unpacked)
+        e.stage_finish(flag)
+
     def step(self, t_end=1e300):
         e = self.eng
         self.hx.allreduce_max(self.dtmax)       # Fluids.cpp:902-913
         e.dt_device(t_end)                      # XFLUIDS.cpp:196-199
         for flag in (1, 2, 3):                  # XFLUIDS.cpp:441-525
-            UI = e.U if flag == 1 else e.U1
-            e.boundary(UI, self.bc)
-            self.halo(UI)
-            e.rk_stage(None, flag)
+            if self.overlap:
+                self.stage_overlapped(flag)
+            else:
+                self.stage_blocking(flag)
 
     def steps(self, n, t_end=1e300):
         for _ in range(n):
