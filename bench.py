@@ -185,6 +185,9 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    if os.environ.get("WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        # torchrun pins OMP_NUM_THREADS=1; the host-side initial condition (OpenMP) gets this rank's share of the cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
     import numpy as np
     import torch
     import torch.distributed as dist

@@ -124,3 +124,54 @@ def test_fused_path_equals_block_calls(case, weno):
     assert abs(t - sum(dts)) <= 1e-15 * t
     assert np.array_equal(a.download(a.U), b.download(b.U))
     assert np.array_equal(a.get_scalar("p"), b.get_scalar("p"))
+
+
+@pytest.mark.parametrize("case,weno", [("shock-tube", 5), ("sbi", 5), ("jet", 5), ("vortex", 5), ("shock-tube", 7)])
+def test_100_steps_vs_oracle(case, weno):
+    """north_star: <= 1e-9 relative L-inf on conserved variables after 100 steps (strict mode, fused graph path) against the
+    CPU oracle (itself bit-exact vs the compiled reference over 100 steps, tests/test_oracle_vs_ref.py)."""
+    import xfgpu
+    g, res = golden(case, weno)
+    o = xfref.Oracle(case, res, weno=weno)
+    o.set_state(g["ic_U"], g["ic_T"]); o.startup()
+    n, dts, t_o = o.run(100)
+    assert n == 100
+    eng = xfgpu.make_engine(case, res, weno=weno, fp_mode=0)
+    E = eng.E
+    mask = xfref.inner_mask(eng.cfg)
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    done, t, err = eng.run(eng.bc, 100)
+    assert (done, err) == (100, 0)
+    e100 = xfgpu.rel_linf(eng.download(eng.U).reshape(-1, E)[mask], o.arr("U").reshape(-1, E)[mask], E)
+    print("\n%s weno%d: rel Linf after 100 steps %.3e, t %.9e vs oracle %.9e" % (case, weno, e100, t, t_o))
+    assert e100 <= 1e-9
+    assert abs(t - t_o) <= 1e-12 * t_o
+    if case in NOCOP:
+        assert e100 == 0.0 and t == t_o
+
+
+def test_freestream_preserved_bitwise_large_block():
+    """Size-independent property at a BASELINE-scale pitch (3-D multi-species, 256 x 64 x 48): a uniform state with the SBI
+    boundary set stays EXACTLY uniform over 3 steps -- any indexing / mask / halo slip in the sweeps, divergence or BC
+    kernels would break the bitwise equality."""
+    import xfgpu
+    res = (256, 64, 48)
+    eng = xfgpu.make_engine("sbi", res, weno=5, fp_mode=0)
+    E, n = eng.E, eng.ncells
+    g, _ = golden("sbi", 5)
+    cell = g["ic_U"].reshape(-1, E)[-1].copy()      # far-field cell of the golden IC (pre-shock N2 at rest)
+    cell[1:4] = [3.0 * cell[0], -2.0 * cell[0], 1.5 * cell[0]]
+    U = np.tile(cell, n)
+    T = np.full(n, float(g["ic_T"][-1]))
+    eng.set_state(U, T)
+    bc = [3, 3, 3, 3, 3, 3]                          # periodic: the uniform flow leaves nothing to the boundary
+    eng.boundary(eng.U, bc)
+    assert eng.update_states(eng.U) == 0
+    U0 = eng.download(eng.U).reshape(-1, E)
+    done, t, err = eng.run(bc, 3)
+    assert (done, err) == (3, 0)
+    U3 = eng.download(eng.U).reshape(-1, E)
+    assert np.array_equal(U3, U0)
+    assert np.array_equal(U3, np.tile(U0[0], (n, 1)))

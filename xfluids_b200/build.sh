@@ -7,7 +7,7 @@ SRC=$HERE/csrc
 OBJ=$HERE/_obj
 mkdir -p "$OBJ"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH ${XF_EXTRA:-}"
 up_to_date() { [ -f "$1" ] && [ -z "$(find "$SRC" "$HERE/../include" -newer "$1" -type f | head -1)" ]; }
 host_up_to_date() { [ -f "$1" ] && [ -z "$(find "$HERE/host" "$HERE/../include" "$HERE/libxfluids_b200.so" -newer "$1" -type f | head -1)" ]; }
 build_host() {

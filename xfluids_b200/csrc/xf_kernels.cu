@@ -384,12 +384,18 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 	}
 }
 
+#ifndef XF_MINB_X
+#define XF_MINB_X 4   // resident blocks per SM the x sweep is compiled for (register cap 65536 / (XF_MINB_X * 128))
+#endif
+#ifndef XF_MINB_YZ
+#define XF_MINB_YZ 2  // same for the y / z sweeps (256 threads per block)
+#endif
 constexpr int XF_TX = 128; // x-sweep: faces (cells) per block
 constexpr int XF_TW = 32;  // y/z sweeps: tile width in x
 constexpr int XF_TF = 8;   // y/z sweeps: faces per tile along the sweep
 
 template <class C, int DIR, int WENO>
-__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
+__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
 {
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
 	extern __shared__ double smem[];

@@ -133,20 +133,22 @@ XF_DEV double xf_get_T(const XfThermo &th, const double *yi, double e, double T0
 // ------------------------------------------------------------------------------------------------
 // WENO5-JS as written in weno5old_BODY (WENO5s_schemes.hpp:12-69) and WENO7-JS (WENO7s_schemes.hpp:8-128)
 // ------------------------------------------------------------------------------------------------
+// Multiplications by 2 and 4 are exact in binary floating point, so  a - 2.0*b  and  fma(-2.0, b, a)  round the same real
+// number once and are bit-identical; those (and only those) products are fused explicitly here, in both build flavours.
 XF_DEV double xf_weno5_body(double v1, double v2, double v3, double v4, double v5)
 {
 	double a1, a2, a3;
-	a1 = v1 - 2.0 * v2 + v3;
+	a1 = fma(-2.0, v2, v1) + v3;                 // v1 - 2.0 * v2 + v3
 	double s1 = 13.0 * a1 * a1;
-	a1 = v1 - 4.0 * v2 + 3.0 * v3;
+	a1 = fma(-4.0, v2, v1) + 3.0 * v3;           // v1 - 4.0 * v2 + 3.0 * v3
 	s1 += 3.0 * a1 * a1;
-	a1 = v2 - 2.0 * v3 + v4;
+	a1 = fma(-2.0, v3, v2) + v4;                 // v2 - 2.0 * v3 + v4
 	double s2 = 13.0 * a1 * a1;
 	a1 = v2 - v4;
 	s2 += 3.0 * a1 * a1;
-	a1 = v3 - 2.0 * v4 + v5;
+	a1 = fma(-2.0, v4, v3) + v5;                 // v3 - 2.0 * v4 + v5
 	double s3 = 13.0 * a1 * a1;
-	a1 = 3.0 * v3 - 4.0 * v4 + v5;
+	a1 = fma(-4.0, v4, 3.0 * v3) + v5;           // 3.0 * v3 - 4.0 * v4 + v5
 	s3 += 3.0 * a1 * a1;
 	s1 += 1.0E-6, s2 += 1.0E-6, s3 += 1.0E-6;
 	a1 = 0.1 * s2 * s2 * s3 * s3;
@@ -154,9 +156,9 @@ XF_DEV double xf_weno5_body(double v1, double v2, double v3, double v4, double v
 	a3 = 0.3 * s1 * s1 * s2 * s2;
 	const double tw1 = 1.0 / (a1 + a2 + a3);
 	a1 = a1 * tw1, a2 = a2 * tw1, a3 = a3 * tw1;
-	s1 = a1 * (2.0 * v1 - 7.0 * v2 + 11.0 * v3);
-	s2 = a2 * (-v2 + 5.0 * v3 + 2.0 * v4);
-	s3 = a3 * (2.0 * v3 + 5.0 * v4 - v5);
+	s1 = a1 * (fma(2.0, v1, -(7.0 * v2)) + 11.0 * v3);   // 2.0 * v1 - 7.0 * v2 + 11.0 * v3
+	s2 = a2 * fma(2.0, v4, 5.0 * v3 - v2);                // -v2 + 5.0 * v3 + 2.0 * v4
+	s3 = a3 * (fma(2.0, v3, 5.0 * v4) - v5);              // 2.0 * v3 + 5.0 * v4 - v5
 	return (s1 + s2 + s3);
 }
 XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v5, double v6, double v7)
@@ -167,10 +169,10 @@ XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v
 	const double S11 = 1.0 / 6.0 * v2 - 6.0 / 6.0 * v3 + 3.0 / 6.0 * v4 + 2.0 / 6.0 * v5;
 	const double S12 = -2.0 / 6.0 * v3 - 3.0 / 6.0 * v4 + 6.0 / 6.0 * v5 - 1.0 / 6.0 * v6;
 	const double S13 = -11.0 / 6.0 * v4 + 18.0 / 6.0 * v5 - 9.0 / 6.0 * v6 + 2.0 / 6.0 * v7;
-	const double S20 = -v1 + 4.0 * v2 - 5.0 * v3 + 2.0 * v4;
-	const double S21 = v3 - 2.0 * v4 + v5;
-	const double S22 = v4 - 2.0 * v5 + v6;
-	const double S23 = 2.0 * v4 - 5.0 * v5 + 4.0 * v6 - 1.0 * v7;
+	const double S20 = fma(2.0, v4, fma(4.0, v2, -v1) - 5.0 * v3);          // -v1 + 4.0 * v2 - 5.0 * v3 + 2.0 * v4
+	const double S21 = fma(-2.0, v4, v3) + v5;                               // v3 - 2.0 * v4 + v5
+	const double S22 = fma(-2.0, v5, v4) + v6;                               // v4 - 2.0 * v5 + v6
+	const double S23 = fma(4.0, v6, fma(2.0, v4, -(5.0 * v5))) - v7;         // 2.0 * v4 - 5.0 * v5 + 4.0 * v6 - 1.0 * v7
 	const double S30 = -v1 + 3.0 * v2 - 3.0 * v3 + v4;
 	const double S31 = -v2 + 3.0 * v3 - 3.0 * v4 + v5;
 	const double S32 = -v3 + 3.0 * v4 - 3.0 * v5 + v6;
@@ -197,12 +199,16 @@ XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v
 // fully unrolled (every field has its own sparse projection), and nine inlined copies of this body push the sweep kernel
 // to ~78 KB of SASS, which showed up in ncu as the top stall reason ("no instruction").
 static __device__ __noinline__ double xf_split_weno5(double av, double u0, double u1, double u2, double u3, double u4, double u5,
-											  double f0, double f1, double f2, double f3, double f4, double f5)
+													 double f0, double f1, double f2, double f3, double f4, double f5)
 {
 	// stencil s=0..5 <-> cells i-2..i+3 ; weno5old_GPU(&pp[3],&mm[3]): plus uses i-2..i+2, minus i+3..i-1
-	const double a0 = av * u0, a1 = av * u1, a2 = av * u2, a3 = av * u3, a4 = av * u4, a5 = av * u5;
-	const double p1 = 0.5 * (f0 + a0), p2 = 0.5 * (f1 + a1), p3 = 0.5 * (f2 + a2), p4 = 0.5 * (f3 + a3), p5 = 0.5 * (f4 + a4);
-	const double m1 = 0.5 * (f5 - a5), m2 = 0.5 * (f4 - a4), m3 = 0.5 * (f3 - a3), m4 = 0.5 * (f2 - a2), m5 = 0.5 * (f1 - a1);
+	// 0.5 * (f + av * u) == 0.5 * f + (0.5 * av) * u bit for bit (scaling by a power of two commutes with rounding), which
+	// needs one multiplication less per stencil point than halving pp and mm separately
+	const double hv = 0.5 * av;
+	const double a0 = hv * u0, a1 = hv * u1, a2 = hv * u2, a3 = hv * u3, a4 = hv * u4, a5 = hv * u5;
+	const double h0 = 0.5 * f0, h1 = 0.5 * f1, h2 = 0.5 * f2, h3 = 0.5 * f3, h4 = 0.5 * f4, h5 = 0.5 * f5;
+	const double p1 = h0 + a0, p2 = h1 + a1, p3 = h2 + a2, p4 = h3 + a3, p5 = h4 + a4;
+	const double m1 = h5 - a5, m2 = h4 - a4, m3 = h3 - a3, m4 = h2 - a2, m5 = h1 - a1;
 	return (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
 }
 static __device__ __noinline__ double xf_split_weno7(double av, double u0, double u1, double u2, double u3, double u4, double u5, double u6, double u7,
