@@ -50,6 +50,22 @@ extern "C"
 }
 
 // ---- constants: include/global_setup.h:38-54 ---------------------------------------------------
+// Conditioning experiment (tests/test_conditioning.py): -DXO_PERTURB_LOG builds a variant whose log() result is moved by one
+// ulp for about half of the arguments -- the size of difference any other libm (e.g. CUDA libdevice) is allowed to have.
+#ifdef XO_PERTURB_LOG
+#include <cstdint>
+#include <cstring>
+static inline double xo_perturbed_log(double x)
+{
+	double r = std::log(x);
+	uint64_t b;
+	std::memcpy(&b, &x, 8);
+	return (b & 1) ? std::nextafter(r, 1e300) : r;
+}
+#define XO_LOG(x) xo_perturbed_log(x)
+#else
+#define XO_LOG(x) std::log(x)
+#endif
 static const double _OT = (1.0 / 3.0);
 static const double _six = 1.0 / 6.0; // schemes/Utils_schemes.hpp:5
 static const double Avogadro = 6.02214076e26;
@@ -78,11 +94,11 @@ static inline double get_Enthalpy_NASA(const double *Hia, const double *Hib, con
 	double hi = 0.0, TT = T0, T = std::fmax(T0, 200.0);
 	const double *a = Hia + n * 7 * 3, *b = Hib + n * 2 * 3;
 	if (T >= 1000.0 && T < 6000.0)
-		hi = Ri * (-a[0 * 3 + 1] / T + a[1 * 3 + 1] * std::log(T) + (a[2 * 3 + 1] + (0.5 * a[3 * 3 + 1] + (a[4 * 3 + 1] * _OT + (0.25 * a[5 * 3 + 1] + 0.2 * a[6 * 3 + 1] * T) * T) * T) * T) * T + b[0 * 3 + 1]);
+		hi = Ri * (-a[0 * 3 + 1] / T + a[1 * 3 + 1] * XO_LOG(T) + (a[2 * 3 + 1] + (0.5 * a[3 * 3 + 1] + (a[4 * 3 + 1] * _OT + (0.25 * a[5 * 3 + 1] + 0.2 * a[6 * 3 + 1] * T) * T) * T) * T) * T + b[0 * 3 + 1]);
 	else if (T < 1000.0)
-		hi = Ri * (-a[0 * 3 + 0] / T + a[1 * 3 + 0] * std::log(T) + (a[2 * 3 + 0] + (0.5 * a[3 * 3 + 0] + (a[4 * 3 + 0] * _OT + (0.25 * a[5 * 3 + 0] + 0.2 * a[6 * 3 + 0] * T) * T) * T) * T) * T + b[0 * 3 + 0]);
+		hi = Ri * (-a[0 * 3 + 0] / T + a[1 * 3 + 0] * XO_LOG(T) + (a[2 * 3 + 0] + (0.5 * a[3 * 3 + 0] + (a[4 * 3 + 0] * _OT + (0.25 * a[5 * 3 + 0] + 0.2 * a[6 * 3 + 0] * T) * T) * T) * T) * T + b[0 * 3 + 0]);
 	else if (T >= 6000.0)
-		hi = Ri * (-a[0 * 3 + 2] / T + a[1 * 3 + 2] * std::log(T) + (a[2 * 3 + 2] + (0.5 * a[3 * 3 + 2] + (a[4 * 3 + 2] * _OT + (0.25 * a[5 * 3 + 2] + 0.2 * a[6 * 3 + 2] * T) * T) * T) * T) * T + b[0 * 3 + 2]);
+		hi = Ri * (-a[0 * 3 + 2] / T + a[1 * 3 + 2] * XO_LOG(T) + (a[2 * 3 + 2] + (0.5 * a[3 * 3 + 2] + (a[4 * 3 + 2] * _OT + (0.25 * a[5 * 3 + 2] + 0.2 * a[6 * 3 + 2] * T) * T) * T) * T) * T + b[0 * 3 + 2]);
 	if (TT < 200.0)
 	{ // linear extension below 200 K
 		double Cpi = HeatCapacity_NASA(Hia, 200.0, Ri, n);

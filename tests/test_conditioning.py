@@ -1,0 +1,55 @@
+"""CPU: how well-conditioned is each config with respect to the ONE place where a GPU build may legally differ from the
+reference's CPU path -- the last bit of log() in the NASA-9 enthalpy (libdevice vs glibc)?
+
+The oracle (bit-exact vs the compiled reference) is run against a copy of itself whose log() is moved by one ulp on about half
+of its arguments.  This bounds what any implementation with a different libm can achieve and is the evidence behind the
+tolerances of tests/test_gpu_parity.py::test_100_steps_vs_oracle:
+  * shock tube, SBI: far inside the north_star tolerances (1e-12 after 1 step, 1e-9 after 100)
+  * under-expanded jet (24x12x12 golden grid: a 10 atm sonic jet through two cells): inside after 1 step (1.6e-14), but the
+    perturbation grows by a factor ~4 per step at first (1e-8 after 10 steps, 6e-7 after 100) -- the reference does not
+    reproduce ITSELF to 1e-9 over 100 steps there under a 1-ulp libm change, so no other implementation can be asked to.
+    (The CUDA build happens to agree with the reference bit for bit over the first 10 steps: libdevice's log matches glibc's
+    far more often than this 50 % perturbation.)"""
+import os
+
+import numpy as np
+import pytest
+
+import xfref
+
+
+def rel_linf_components(a, b, E):
+    den = np.abs(b).max(axis=0)
+    den[1:4] = den[1:4].max()
+    return np.abs(a - b).max(axis=0) / np.maximum(den, 1e-300)
+
+
+def run_pair(case, weno, nsteps):
+    g = np.load(os.path.join(xfref.GOLDEN, "%s_w%d.npz" % (case, weno)))
+    res = tuple(int(x) for x in g["res"])
+    out = []
+    for so in (xfref.ORACLE_SO, os.path.join(os.path.dirname(xfref.ORACLE_SO), "liboracle_plog.so")):
+        o = xfref.Oracle(case, res, weno=weno, so=so)
+        o.set_state(g["ic_U"], g["ic_T"])
+        o.startup()
+        n, _, _ = o.run(nsteps)
+        assert n == nsteps
+        E = o.cfg.Emax
+        out.append(o.arr("U").reshape(-1, E)[xfref.inner_mask(o.cfg)].copy())
+    return rel_linf_components(out[1], out[0], E)
+
+
+@pytest.mark.parametrize("case,nsteps,bound", [("shock-tube", 1, 1e-12), ("sbi", 1, 1e-12), ("jet", 1, 1e-12),
+                                                ("shock-tube", 100, 1e-9), ("sbi", 100, 1e-9)])
+def test_one_ulp_log_stays_inside_north_star_tolerance(case, nsteps, bound):
+    e = run_pair(case, 5, nsteps)
+    print(case, nsteps, e)
+    assert e.max() <= bound
+
+
+def test_jet_amplifies_one_ulp_beyond_1e9_within_100_steps():
+    """Documents the conditioning of the jet config: if this ever starts failing (the perturbation stays below 1e-9), tighten
+    JET_100_BOUND in tests/test_gpu_parity.py back to the north_star value."""
+    e = run_pair("jet", 5, 100)
+    print("jet 100 steps, 1-ulp log perturbation:", e)
+    assert 1e-9 < e.max() < 5e-6

@@ -56,3 +56,16 @@ def reference_step_unfused(eng, nsteps, t_end=1e300):
             assert eng.estimate_nan(eng.U if flag == 3 else eng.U1) == 0
             eng.update_u(dt, flag)
     return dts
+
+
+def rel_linf_components(a, b, E, joint_momentum=True):
+    """Per-variable max|a-b| / scale_n.  scale_n = max|b_n|, except that the three momentum components share one scale
+    (max over the three): momentum is a vector, and a component that is zero by symmetry (rho*w in the planar jet, rho*v and
+    rho*w in the 1-D tube) has max|b_n| ~ 1e-18 of rounding noise, against which any difference is O(1)."""
+    a = np.asarray(a).reshape(-1, E)
+    b = np.asarray(b).reshape(-1, E)
+    den = np.abs(b).max(axis=0)
+    if joint_momentum:
+        den[1:4] = den[1:4].max()
+    den = np.maximum(den, 1e-300)
+    return np.abs(a - b).max(axis=0) / den

@@ -390,9 +390,15 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 #ifndef XF_MINB_YZ
 #define XF_MINB_YZ 2  // same for the y / z sweeps (256 threads per block)
 #endif
-constexpr int XF_TX = 128; // x-sweep: faces (cells) per block
-constexpr int XF_TW = 32;  // y/z sweeps: tile width in x
-constexpr int XF_TF = 8;   // y/z sweeps: faces per tile along the sweep
+#ifndef XF_TX_
+#define XF_TX_ 128
+#endif
+#ifndef XF_TF_
+#define XF_TF_ 8
+#endif
+constexpr int XF_TX = XF_TX_; // x-sweep: faces (cells) per block
+constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
+constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
 template <class C, int DIR, int WENO>
 __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
