@@ -153,14 +153,14 @@ def test_100_steps_vs_oracle(case, weno):
     # jet: the config itself amplifies a 1-ulp log() difference to 6e-7 within 100 steps (tests/test_conditioning.py shows the
     # reference's own algorithm doing so on the CPU), so the north_star figure is not attainable by any build with another libm
     assert e100 <= (JET_100_BOUND if case == "jet" else 1e-9)
-    assert abs(t - t_o) <= 1e-12 * t_o
+    assert abs(t - t_o) <= (JET_100_BOUND if case == "jet" else 1e-12) * t_o
     if case in NOCOP:
         assert e100 == 0.0 and t == t_o
 
 
 def test_freestream_preserved_bitwise_large_block():
-    """Size-independent property at a BASELINE-scale pitch (3-D multi-species, 256 x 64 x 48): a uniform state with the SBI
-    boundary set stays EXACTLY uniform over 3 steps -- any indexing / mask / halo slip in the sweeps, divergence or BC
+    """Size-independent property at a BASELINE-scale pitch (3-D multi-species, 256 x 64 x 48): a uniform moving state in a periodic
+    box stays EXACTLY uniform over 3 steps -- any indexing / mask / halo slip in the sweeps, divergence or BC
     kernels would break the bitwise equality."""
     import xfgpu
     res = (256, 64, 48)
@@ -179,5 +179,8 @@ def test_freestream_preserved_bitwise_large_block():
     done, t, err = eng.run(bc, 3)
     assert (done, err) == (3, 0)
     U3 = eng.download(eng.U).reshape(-1, E)
-    assert np.array_equal(U3, U0)
-    assert np.array_equal(U3, np.tile(U0[0], (n, 1)))
+    # every cell performs the same arithmetic on the same numbers: the field must stay uniform BIT FOR BIT (the value itself may
+    # move by an ulp per stage: 0.75*U + 0.25*U and (U + 2U)*(1/3) are not exact identities in floating point)
+    assert np.array_equal(U3, np.tile(U3[0], (n, 1)))
+    assert np.array_equal(U0, np.tile(U0[0], (n, 1)))
+    assert np.abs(U3[0] - U0[0]).max() <= 1e-14 * np.abs(U0[0]).max()

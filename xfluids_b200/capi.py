@@ -8,7 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libxfluids_b200.so")
+    # XF_LIB: an alternative build of the same library (kernel tuning experiments); default: the in-tree build
+    return os.environ.get("XF_LIB") or os.path.join(_HERE, "libxfluids_b200.so")
 
 
 class XfError(RuntimeError):

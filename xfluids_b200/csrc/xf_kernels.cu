@@ -51,6 +51,9 @@ __device__ __forceinline__ bool xf_bad(double x) { return (x < 0) || isnan(x) ||
 // Both end in the same epilogue.
 // ---------------------------------------------------------------------------------------------
 constexpr int XF_NEWTON_FAST = 3;
+#ifndef XF_PRIM_MINB
+#define XF_PRIM_MINB 6   // resident 128-thread blocks per SM k_prim is compiled for (register cap 65536 / (128 * XF_PRIM_MINB))
+#endif
 
 template <class C>
 struct PrimCell
@@ -59,28 +62,45 @@ struct PrimCell
 	double yi[C::NS];
 };
 
-// one limited Newton step of get_T (Mixing_device.h:171-193); returns true when the stop criterion is met
+// The limited Newton iteration of get_T (Mixing_device.h:171-193) from iteration `it` on, written around ONE evaluation
+// site of the species enthalpies / mixture Cp (the loop is not unrolled; the evaluation that follows the last update is the
+// one the epilogue needs, at the final T).  Returns false when `limit` iterations have been done without meeting the stop
+// criterion and `park` is set (T then holds the iterate to resume from); with park == false the limit is the reference's
+// 100-iteration cap, after which T is used as it is.
 template <class C>
-XF_DEV bool xf_newton_step(const XfThermo &th, const double *yi, double e, double R, double &T)
+XF_DEV bool xf_newton(const XfThermo &th, const double *yi, double e, double R, double &T, int it, int limit, bool park, double *hi, double &Cp)
 {
-	double hi[C::NS];
-	xf_species_h<C>(th, T, hi);
-	double h = 0.0;
+	bool conv = false;
+#pragma unroll 1
+	for (;;)
+	{
+		if (!conv && it == limit)
+		{
+			if (park)
+				return false;
+			conv = true;
+		}
+		xf_species_h<C>(th, T, hi);
+		Cp = xf_mix_cp<C>(th, yi, T);
+		if (conv)
+			return true;
+		double h = 0.0;
 #pragma unroll
-	for (int n = 0; n < C::NS; n++)
-		h += hi[n] * yi[n];
-	const double Cp = xf_mix_cp<C>(th, yi, T);
-	const double func_T = h - R * T - e;
-	const double dfunc_T = Cp - R;
-	double df = xf_min(func_T / (dfunc_T + 1.0e-30), 1e-3 * T);
-	df = xf_max(df, -1e-2 * T);
-	T = T - df;
-	return fabs(df) <= 1.0e-6;
+		for (int n = 0; n < C::NS; n++)
+			h += hi[n] * yi[n];
+		const double func_T = h - R * T - e;
+		const double dfunc_T = Cp - R;
+		double df = xf_min(func_T / (dfunc_T + 1.0e-30), 1e-3 * T);
+		df = xf_max(df, -1e-2 * T);
+		T = T - df;
+		it++;
+		conv = fabs(df) <= 1.0e-6;
+	}
 }
 
 template <class C>
-XF_DEV void prim_epilogue(const XfDev &d, const XfThermo &th, long long id, bool inner, const PrimCell<C> &pc, double T, int flags,
-						  double *dtm, double *glf)
+XF_DEV void prim_epilogue(const XfDev &d, const XfThermo &th, long long id, bool inner, const PrimCell<C> &pc, double T, const double *hi, double Cp,
+						  int flags, double *dtm, double *glf)
 {
 	constexpr int NS = C::NS, NC = C::NC;
 	const double rho = pc.rho, rho1 = pc.rho1, u = pc.u, v = pc.v, w = pc.w, q2 = pc.q2;
@@ -90,15 +110,13 @@ XF_DEV void prim_epilogue(const XfDev &d, const XfThermo &th, long long id, bool
 		const double R = pc.R, Wm = pc.Wm;
 		const double *yi = pc.yi;
 		p = rho * R * T;
-		const double Cp = xf_mix_cp<C>(th, yi, T);
+		// Cp = get_CopCp(T), hi = species enthalpies at T: evaluated by the caller (xf_newton's last evaluation)
 		// 4-argument get_CopGamma (Mixing_device.h:114-126)
 		const double CopW = 1.0 / Wm;
 		const double g4 = Cp / (Cp - th.Ru / CopW);
 		gamma = (g4 > 1.0) ? g4 : -1.0;
 		const double H = (pc.U4 + p) * rho1;
 		// per-cell pieces of ReconstructSoundSpeed (Utils_device.hpp:102-131)
-		double hi[NS];
-		xf_species_h<C>(th, T, hi);
 		const double Cv = Cp - th.Ru * Wm;
 		const double g3 = Cp / Cv; // 3-argument get_CopGamma
 		const double prho = p / rho;
@@ -179,7 +197,7 @@ __device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
 }
 
 template <class C>
-__global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0, long long lin1)
+__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0, long long lin1)
 {
 	const long long lin = lin0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const bool active = lin < lin1 && int(lin % d.Xp) < d.Xmax;
@@ -221,7 +239,7 @@ __global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__re
 		pc.u = pc.U1 * pc.rho1, pc.v = pc.U2 * pc.rho1, pc.w = pc.U3 * pc.rho1;
 		pc.q2 = pc.u * pc.u + pc.v * pc.v + pc.w * pc.w;
 		pc.tme = pc.U4 * pc.rho1 - 0.5 * pc.q2;
-		double T = 0.0;
+		double T = 0.0, Cp = 0.0, hi[NS];
 		bool done = true;
 		if constexpr (C::COP)
 		{
@@ -231,13 +249,7 @@ __global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__re
 				Wm += pc.yi[n] * th._Wi[n];
 			pc.Wm = Wm, pc.R = Wm * th.Ru;
 			T = d.T[id];
-			done = false;
-			for (int it = 1; it <= XF_NEWTON_FAST; it++)
-				if (xf_newton_step<C>(th, pc.yi, pc.tme, pc.R, T))
-				{
-					done = true;
-					break;
-				}
+			done = xf_newton<C>(th, pc.yi, pc.tme, pc.R, T, 0, XF_NEWTON_FAST, true, hi, Cp);
 			if (!done)
 			{ // park: T after XF_NEWTON_FAST steps; k_prim_hard resumes at iteration XF_NEWTON_FAST + 1
 				d.T[id] = T;
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(128) k_prim(XfDev d, XfThermo th, double *__re
 			}
 		}
 		if (done)
-			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, flags, dtm, glf);
+			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, hi, Cp, flags, dtm, glf);
 	}
 	prim_reduce(d, flags, dtm, glf);
 }
@@ -280,11 +292,9 @@ __global__ void __launch_bounds__(128) k_prim_hard(XfDev d, XfThermo th, const d
 			for (int n = 0; n < NS; n++)
 				Wm += pc.yi[n] * th._Wi[n];
 			pc.Wm = Wm, pc.R = Wm * th.Ru;
-			double T = d.T[id];
-			for (int it = XF_NEWTON_FAST + 1; it < 101; it++)
-				if (xf_newton_step<C>(th, pc.yi, pc.tme, pc.R, T))
-					break;
-			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, flags, dtm, glf);
+			double T = d.T[id], Cp, hi[NS];
+			xf_newton<C>(th, pc.yi, pc.tme, pc.R, T, XF_NEWTON_FAST, 100, false, hi, Cp);
+			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, hi, Cp, flags, dtm, glf);
 		}
 		prim_reduce(d, flags, dtm, glf);
 	}
@@ -492,6 +502,22 @@ __device__ __forceinline__ bool inner_cell(const XfDev &d, long long &id)
 	id = ((k + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
 	return true;
 }
+// Block order of the fused divergence + update: consecutive blocks walk along z for one (x chunk, y) column, so that the
+// lower z-face flux a block needs (Fw_z at k-1) was read by the block just before it and the lower y-face flux by a block
+// Zi launches earlier (~28 MB of traffic at 512^3) -- both still in L2.  With the x-fastest order of inner_cell the reuse
+// distance of Fw_z is one whole plane of every array (~120 MB) and the k-1 values come from DRAM a second time.
+__device__ __forceinline__ bool inner_cell_zfast(const XfDev &d, long long &id)
+{
+	const long long b = blockIdx.x;
+	const int k = int(b % d.Zi);
+	const long long r = b / d.Zi;
+	const int j = int(r % d.Yi);
+	const int i = int(r / d.Yi) * blockDim.x + threadIdx.x;
+	if (i >= d.Xi)
+		return false;
+	id = ((long long)(k + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
+	return true;
+}
 __device__ __forceinline__ double lu_of(const XfDev &d, long long o)
 {
 	double LU0 = 0.0;
@@ -527,7 +553,7 @@ __global__ void __launch_bounds__(256) k_rk(XfDev d, double *__restrict__ U, dou
 											double dt_host, const double *__restrict__ dt_dev, int flag, int guard)
 {
 	long long id;
-	if (!inner_cell(d, id))
+	if (FUSED_LU ? !inner_cell_zfast(d, id) : !inner_cell(d, id))
 		return;
 	const double dt = dt_dev ? *dt_dev : dt_host;
 	bool bad = false;
@@ -865,7 +891,8 @@ int launch_rk(const XfDev &d, int E_, double *U, double *U1, const double *LU, d
 	const long long n = (long long)d.Xi * d.Yi * d.Zi;
 	if (fused)
 	{
-		XF_DISPATCH_E(E_, k_rk<E, true><<<nblk(n, 256), 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
+		const long long nb = (long long)((d.Xi + 255) / 256) * d.Yi * d.Zi; // one block per (x chunk, y, z), z fastest
+		XF_DISPATCH_E(E_, k_rk<E, true><<<(unsigned)nb, 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
 	}
 	else
 	{
