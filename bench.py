@@ -175,7 +175,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sbi", choices=sorted(WORKLOADS))
-    ap.add_argument("--grid", default=None, help="nx,ny,nz inner cells per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--grid", default=None, help="nx,ny,nz inner cells (per GPU when weak, of the whole box when strong; default: the workload's BASELINE size)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: weak for sbi (z extent grows with N), strong for jet (fixed box cut in z)")
     ap.add_argument("--fp", type=int, default=0, help="0 strict (parity mode, default), 1 FMA contraction in the sweeps")
     ap.add_argument("--weno", type=int, default=5)
     ap.add_argument("--e2e-steps", type=int, default=None)
@@ -207,9 +208,10 @@ def main():
 
     w = WORKLOADS[args.workload]
     grid = tuple(int(x) for x in args.grid.split(",")) if args.grid else w["grid"]
+    scaling = args.scaling or ("strong" if args.workload == "jet" else "weak")
     cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=LLF", "-fp=%d" % args.fp]
     if world > 1:
-        cli += ["-mpi=1,1,%d" % world, "-mpi-s=weak"]
+        cli += ["-mpi=1,1,%d" % world, "-mpi-s=%s" % scaling]
     setup = host.Setup(os.path.join(REPO, "settings", w["json"]), cli, rank=rank, nranks=world)
     E = setup.Emax
     ncells = setup.ncells
@@ -343,8 +345,8 @@ def main():
 
     if rank == 0:
         line = {"metric": "cell-updates/sec (Mcell*stage/s)", "value": value, "unit": "Mcell*stage/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "grid_per_gpu": list(grid), "emax": E, "weno": args.weno, "flux_splitting": "LLF",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "flux_splitting": "LLF",
                            "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
                            "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
                            "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % (eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9),

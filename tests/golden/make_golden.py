@@ -15,7 +15,21 @@ import xfref
 GRID = {"shock-tube": (400, 0, 0), "vortex": (32, 32, 0), "riemann": (32, 32, 0), "sbi": (24, 12, 12), "jet": (24, 12, 12)}
 VARIANTS = [("shock-tube", 5), ("shock-tube", 7), ("vortex", 5), ("riemann", 5), ("sbi", 5), ("sbi", 7), ("jet", 5)]
 
+# flux-splitting variants other than LLF (Artificial_type 1 = ROE, 3 = GLF; the GLF running maximum is never reset, so 10 steps
+# exercise that driver-state semantic): tests/golden/<case>_w5_<alpha>.npz
+ALPHA_VARIANTS = [("vortex", 5, 3), ("vortex", 5, 1), ("sbi", 5, 3), ("sbi", 5, 1)]
+
 if __name__ == "__main__":
+    for case, weno, alpha in ALPHA_VARIANTS:
+        res = GRID[case]
+        A, meta, out = xfref.run_ref(case, res, 10, dump_steps=(1, 10), weno=weno, stage_dump=True, alpha=alpha)
+        assert "ORACLE_TIMING" in out and "error=0" in out, out[-2000:]
+        np.savez_compressed(os.path.join(xfref.GOLDEN, "%s_w%d_%s.npz" % (case, weno, xfref.ALPHA_NAME[alpha].lower())), res=np.array(res), weno=weno, alpha=alpha,
+                            ic_U=A["ic_U"], ic_T=A["ic_T"], U_step1=A["U_step1"], U_step10=A["U_step10"], T_step10=A["T_step10"],
+                            s1_LU=A["s1_LU"], dt=np.array(meta["dt"]))
+        print(case, weno, xfref.ALPHA_NAME[alpha], "ok", meta["dt"][:2])
+    if "--alpha-only" in sys.argv:
+        sys.exit(0)
     for case, weno in VARIANTS:
         res = GRID[case]
         A, meta, out = xfref.run_ref(case, res, 10, dump_steps=(1, 10), weno=weno, stage_dump=True)

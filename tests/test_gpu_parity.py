@@ -184,3 +184,98 @@ def test_freestream_preserved_bitwise_large_block():
     assert np.array_equal(U3, np.tile(U3[0], (n, 1)))
     assert np.array_equal(U0, np.tile(U0[0], (n, 1)))
     assert np.abs(U3[0] - U0[0]).max() <= 1e-14 * np.abs(U0[0]).max()
+
+
+@pytest.mark.parametrize("case,alpha", [("vortex", 3), ("vortex", 1), ("sbi", 3), ("sbi", 1)])
+def test_other_splittings_vs_reference_golden(case, alpha):
+    """ROE (1) and GLF (3) artificial viscosity through the fused path, 1 and 10 steps against the unmodified reference's output.
+    GLF uses the running maximum of |lambda| that is never reset between steps (ConVenction_block.hpp:115-170)."""
+    import xfgpu
+    g = np.load(os.path.join(xfref.GOLDEN, "%s_w5_%s.npz" % (case, xfref.ALPHA_NAME[alpha].lower())))
+    res = tuple(int(x) for x in g["res"])
+    eng = xfgpu.make_engine(case, res, weno=5, alpha=alpha, fp_mode=0)
+    E = eng.E
+    mask = xfref.inner_mask(eng.cfg)
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    done, t, err = eng.run(eng.bc, 1)
+    assert (done, err) == (1, 0)
+    e1 = xfgpu.rel_linf(eng.download(eng.U).reshape(-1, E)[mask], g["U_step1"].reshape(-1, E)[mask], E)
+    done, t, err = eng.run(eng.bc, 9)
+    assert (done, err) == (9, 0)
+    U10 = eng.download(eng.U)
+    e10 = xfgpu.rel_linf(U10.reshape(-1, E)[mask], g["U_step10"].reshape(-1, E)[mask], E)
+    print("\n%s alpha=%s: rel Linf step1 %.3e step10 %.3e" % (case, xfref.ALPHA_NAME[alpha], e1, e10))
+    if case in NOCOP:
+        assert np.array_equal(U10, g["U_step10"])
+    else:
+        assert e1 <= 1e-12 and e10 <= 1e-9
+
+
+@pytest.mark.parametrize("case,bc", [("vortex", [4, 6, 5, 4, 2, 2]), ("riemann", [5, 4, 4, 6, 1, 1]), ("riemann", [2, 3, 3, 2, 1, 1]),
+                                      ("sbi", [4, 1, 2, 4, 6, 5])])
+def test_wall_and_mixed_boundaries_vs_oracle(case, bc):
+    """nslipWall / viscWall / slipWall (the latter two act in x only and are no-ops in y and z, BCs_kernels.hpp:167-171,242-246)
+    and mixed face types: 5 steps against the oracle, ghost cells included."""
+    import xfgpu
+    g, res = golden(case, 5)
+    o = xfref.Oracle(case, res, weno=5)
+    for i, b in enumerate(bc):
+        o.cfg.bc[i] = b
+    o.set_state(g["ic_U"], g["ic_T"]); o.startup()
+    n, dts, t_o = o.run(5)
+    assert n == 5
+    eng = xfgpu.make_engine(case, res, weno=5, fp_mode=0)
+    E = eng.E
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, bc)
+    assert eng.update_states(eng.U) == 0
+    done, t, err = eng.run(bc, 5)
+    assert (done, err) == (5, 0)
+    U = eng.download(eng.U)
+    if case in NOCOP:
+        assert np.array_equal(U, o.arr("U")) and t == t_o
+    else:
+        assert xfgpu.rel_linf(U, o.arr("U"), E) <= 1e-12      # all cells, ghosts too
+
+
+def test_guards_raise_flags_like_the_reference():
+    """The three guard kernels (EstimateYiKernel / EstimatePrimitiveVarKernel, Estimate_kernels.hpp:5-162; EstimateFluidNANKernel,
+    Fluids.cpp:47-87) only flag: rho < 0 / NaN -> flags[0] and [1]; NaN in LU or U -> flags[2]; ghost cells are not inspected."""
+    import xfgpu
+    g, res = golden("sbi", 5)
+    eng = xfgpu.make_engine("sbi", res, weno=5)
+    E, cfg = eng.E, eng.cfg
+    inner_id = (cfg.Bw_Z * cfg.Ymax + cfg.Bw_Y) * cfg.Xmax + cfg.Bw_X + 1
+    # clean state: no flags
+    eng.set_state(g["ic_U"], g["ic_T"]); eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0 and eng.error_flags()[:3] == [0, 0, 0]
+    # negative density in an inner cell
+    U = g["ic_U"].reshape(-1, E).copy()
+    U[inner_id, 0] = -U[inner_id, 0]
+    eng.set_state(U.ravel(), g["ic_T"])
+    assert eng.update_states(eng.U) == 1
+    f = eng.error_flags()
+    assert f[0] == 1 and f[1] == 1
+    eng.L.check(eng.L.dll.xf_clear_errors(eng.ctx))
+    # the same in a ghost cell: not inspected
+    U = g["ic_U"].reshape(-1, E).copy()
+    U[0, 0] = -U[0, 0]
+    eng.set_state(U.ravel(), g["ic_T"])
+    assert eng.update_states(eng.U) == 0
+    # NaN in LU -> EstimateFluidNAN
+    eng.set_state(g["ic_U"], g["ic_T"]); eng.boundary(eng.U, eng.bc); eng.update_states(eng.U); eng.get_lu(eng.U)
+    assert eng.estimate_nan(eng.U1) == 0
+    LU = eng.download(eng.LU).reshape(-1, E)
+    LU[inner_id, 3] = np.nan
+    eng.upload(eng.LU, LU.ravel())
+    assert eng.estimate_nan(eng.U1) == 1 and eng.error_flags()[2] == 1
+    # xf_run stops and reports XF_ERR_NUMERIC when a guard fires
+    eng.L.check(eng.L.dll.xf_clear_errors(eng.ctx))
+    U = g["ic_U"].reshape(-1, E).copy()
+    U[inner_id, 4] = np.nan
+    eng.set_state(U.ravel(), g["ic_T"]); eng.boundary(eng.U, eng.bc); eng.update_states(eng.U)
+    eng.L.check(eng.L.dll.xf_clear_errors(eng.ctx))
+    done, t, err = eng.run(eng.bc, 3)
+    assert err == 1 and done <= 3

@@ -33,3 +33,17 @@ def test_oracle_matches_reference_golden(case, weno):
     assert np.array_equal(o.arr("U"), g["U_step10"])
     assert np.array_equal(o.arr("T"), g["T_step10"])
     assert not o.flags().any()
+
+
+@pytest.mark.parametrize("case,alpha", [("vortex", 3), ("vortex", 1), ("sbi", 3), ("sbi", 1)])
+def test_oracle_matches_reference_golden_other_splittings(case, alpha):
+    """ROE (Artificial_type 1) and GLF (3; running maximum never reset between steps, ConVenction_block.hpp:115-170)."""
+    g = np.load(os.path.join(xfref.GOLDEN, "%s_w5_%s.npz" % (case, xfref.ALPHA_NAME[alpha].lower())))
+    res = tuple(int(x) for x in g["res"])
+    o = xfref.Oracle(case, res, weno=5, alpha=alpha)
+    o.set_state(g["ic_U"], g["ic_T"])
+    assert o.startup() == 0
+    n, dts, t = o.run(10)
+    assert n == 10 and np.array_equal(np.array(dts), g["dt"][:10])
+    assert np.array_equal(o.arr("U"), g["U_step10"])
+    assert np.array_equal(o.arr("T"), g["T_step10"])

@@ -182,13 +182,23 @@ def make_cfg(case, res, weno=5, alpha=2, mz=1):
 
 
 # ---- compiled reference (oracle/_ref) ---------------------------------------------------------------
-def ref_available(case, weno=5, mode="parity"):
-    return os.path.exists(os.path.join(REF_DIR, "%s_w%d_%s" % (case, weno, mode), "XFLUIDS"))
+ALPHA_NAME = {1: "ROE", 2: "LLF", 3: "GLF"}
 
 
-def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None):
+def ref_dir(case, weno=5, mode="parity", alpha=2):
+    tag = "%s_w%d_%s" % (case, weno, mode)
+    if alpha != 2:
+        tag += "_" + ALPHA_NAME[alpha]
+    return os.path.join(REF_DIR, tag)
+
+
+def ref_available(case, weno=5, mode="parity", alpha=2):
+    return os.path.exists(os.path.join(ref_dir(case, weno, mode, alpha), "XFLUIDS"))
+
+
+def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None, alpha=2):
     """Run the compiled reference; returns (dict of arrays, meta dict, stdout)."""
-    d = os.path.join(REF_DIR, "%s_w%d_%s" % (case, weno, mode))
+    d = ref_dir(case, weno, mode, alpha)
     out = outdir or tempfile.mkdtemp(prefix="xfref_")
     env = dict(os.environ, XF_NSTEPS=str(nsteps), XF_DUMP_DIR=out, XF_DUMP_STEPS=",".join(map(str, dump_steps)),
                XF_DUMP_STAGE="1" if stage_dump else "0", XF_DUMP_T="1" if dump_T else "0")
