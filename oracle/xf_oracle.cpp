@@ -14,7 +14,7 @@
 //
 // Compile-time macros of the reference become run-time fields of xo_cfg:
 //   COP -> cop, GhostSpecies -> ghost_species, NUM_SPECIES -> NS, Emax, NUM_COP -> NCOP,
-//   SCHEME_ORDER -> weno (5|7), Artificial_type -> alpha (1 ROE, 2 LLF, 3 GLF), NCOP_Gamma.
+//   SCHEME_ORDER -> weno (5|6|7; 6 = WENO-CU6), Artificial_type -> alpha (1 ROE, 2 LLF, 3 GLF), NCOP_Gamma.
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
@@ -32,6 +32,7 @@ extern "C"
 		int DimX, DimY, DimZ;
 		int NS, Emax, NCOP;
 		int cop, ghost_species, weno, alpha;
+		int positivity; // equations.PositivityPreserving (read_json.cpp:68)
 		double dx, dy, dz, _dx, _dy, _dz, CFL, ncop_gamma;
 		int bc[6];
 		const double *Hia, *Hib, *Ri, *_Wi; // NASA-9 tables Hia[n*21+m*3+range], Hib[n*6+m*3+range]; Ri=Ru/Wi; _Wi=1/Wi
@@ -623,6 +624,58 @@ static inline double weno5old_GPU(const double *f, const double *m)
 	double temm = weno5old_BODY(m[3], m[2], m[1], m[0], m[-1]);
 	return (temf + temm) * _six;
 }
+// ---- schemes/WENO6s_schemes.hpp:5-78 (WENO-CU6, SCHEME_ORDER == 6); constants Utils_schemes.hpp:5-15, global_setup.h:36-37
+static const double _sxtn = 1.0 / 16.0, _twfr = 1.0 / 24.0, _ohtz = 1.0 / 120.0, _ohff = 1.0 / 144.0, _ftss = 1.0 / 5760.0;
+static const double wu6a2a2 = 13.0 / 3.0, wu6a3a3 = 3129.0 / 80.0, wu6a4a4 = 87617.0 / 140.0, wu6a3a5 = 14127.0 / 224.0, wu6a5a5 = 252337135.0 / 16128.0;
+static inline double WENOCU6_BODY(const double v1, const double v2, const double v3, const double v4, const double v5, const double v6, const double epsilon)
+{
+	double s11 = v1 - 2.0 * v2 + v3;
+	double s12 = v1 - 4.0 * v2 + 3.0 * v3;
+	double s1 = 13.0 * s11 * s11 + 3.0 * s12 * s12;
+	double s21 = v2 - 2.0 * v3 + v4;
+	double s22 = v2 - v4;
+	double s2 = 13.0 * s21 * s21 + 3.0 * s22 * s22;
+	double s31 = v3 - 2.0 * v4 + v5;
+	double s32 = 3.0 * v3 - 4.0 * v4 + v5;
+	double s3 = 13.0 * s31 * s31 + 3.0 * s32 * s32;
+	double tau61 = (259.0 * v6 - 1895.0 * v5 + 6670.0 * v4 - 2590.0 * v3 - 2785.0 * v2 + 341.0 * v1) * _ftss;
+	double tau62 = -(v5 - 12.0 * v4 + 22.0 * v3 - 12.0 * v2 + v1) * _sxtn;
+	double tau63 = -(7.0 * v6 - 47.0 * v5 + 94.0 * v4 - 70.0 * v3 + 11.0 * v2 + 5.0 * v1) * _ohff;
+	double tau64 = (v5 - 4.0 * v4 + 6.0 * v3 - 4.0 * v2 + v1) * _twfr;
+	double tau65 = -(-v6 + 5.0 * v5 - 10.0 * v4 + 10.0 * v3 - 5.0 * v2 + v1) * _ohtz;
+	double a1a1 = 1.0, a2a2 = wu6a2a2, a1a3 = 0.5, a3a3 = wu6a3a3, a2a4 = 4.2;
+	double a1a5 = 0.125, a4a4 = wu6a4a4, a3a5 = wu6a3a5, a5a5 = wu6a5a5;
+	double s6 = (tau61 * tau61 * a1a1 + tau62 * tau62 * a2a2 + tau61 * tau63 * a1a3 + tau63 * tau63 * a3a3 + tau62 * tau64 * a2a4 + tau61 * tau65 * a1a5 + tau64 * tau64 * a4a4 + tau63 * tau65 * a3a5 + tau65 * tau65 * a5a5) * 12.0;
+	double s55 = (s1 + s3 + 4.0 * s2) * _six;
+	double s5 = std::fabs(s6 - s55);
+	double r0 = 20.0;
+	double r1 = r0 + s5 / (s1 + epsilon);
+	double r2 = r0 + s5 / (s2 + epsilon);
+	double r3 = r0 + s5 / (s3 + epsilon);
+	double r4 = r0 + s5 / (s6 + epsilon);
+	double a1 = 0.05 * r1;
+	double a2 = 0.45 * r2;
+	double a3 = 0.45 * r3;
+	double a4 = 0.05 * r4;
+	double tw1 = 1.0 / (a1 + a2 + a3 + a4);
+	double w1 = a1 * tw1;
+	double w2 = a2 * tw1;
+	double w3 = a3 * tw1;
+	double w4 = a4 * tw1;
+	double temp = 0.0;
+	temp += w1 * (2.0 * v1 - 7.0 * v2 + 11.0 * v3);
+	temp += w2 * (-v2 + 5.0 * v3 + 2.0 * v4);
+	temp += w3 * (2.0 * v3 + 5.0 * v4 - v5);
+	temp += w4 * (11.0 * v4 - 7.0 * v5 + 2.0 * v6);
+	return temp;
+}
+static inline double WENOCU6_GPU(const double *f, const double *m, double delta)
+{
+	const double epsilon = 1.e-8 * delta * delta;
+	double temf = WENOCU6_BODY(f[-2], f[-1], f[0], f[1], f[2], f[3], epsilon);
+	double temm = WENOCU6_BODY(m[3], m[2], m[1], m[0], m[-1], m[-2], epsilon);
+	return (temf + temm) * _six;
+}
 // ---- schemes/WENO7s_schemes.hpp:8-128 (the _P and _M bodies are identical after the v1..v7 pick)
 static inline double weno7_BODY(const double v1, const double v2, const double v3, const double v4, const double v5, const double v6, const double v7)
 {
@@ -742,7 +795,9 @@ static void ReconstructFlux(const xo_cfg &c, const xo_state &s, int dir, const d
 							pp[m + 3] = 0.5 * (ff[m + 3] + artificial_viscosity * uf[m + 3]);
 							mm[m + 3] = 0.5 * (ff[m + 3] - artificial_viscosity * uf[m + 3]);
 						}
-						f_flux = weno5old_GPU(&pp[3], &mm[3]);
+						// WENO_GPU (schemes_device.hpp:13-20): weno5old for SCHEME_ORDER 5, WENO-CU6 for 6 (dl = the sweep's mesh width,
+						// ConVenction_block.hpp:233,267,301)
+						f_flux = c.weno == 6 ? WENOCU6_GPU(&pp[3], &mm[3], dir == 0 ? c.dx : (dir == 1 ? c.dy : c.dz)) : weno5old_GPU(&pp[3], &mm[3]);
 					}
 					RoeAverageRight(c, dir, n, eigen_lr, rs);
 					for (int n1 = 0; n1 < E; n1++)
@@ -754,6 +809,76 @@ static void ReconstructFlux(const xo_cfg &c, const xo_state &s, int dir, const d
 					for (int n1 = 0; n1 < E; n1++)
 						fluxl += _p[n1][n];
 					Fwall[E * id_l + n] = fluxl;
+				}
+			}
+}
+
+// ---- FDM_Method/positive-definite_eigen/PositivityPreserving_kernels.hpp:5-76 (K8), launched over the inner cells
+// (ConVenction_block.hpp:330-410): id_l = the inner cell, id_r = its +dir neighbour, so the face below the first inner cell
+// is never limited.  Reproduced as written, including `FF[n]` (not FF[nn]) inside the species loop.
+static void PositivityPreserving(const xo_cfg &c, int dir, const double *UI, const double *Fl, double *Fwall, const double lambda_0, const double lambda)
+{
+	const int E = c.Emax, NUM_COP = c.NCOP;
+	const ptrdiff_t st = dir == 0 ? 1 : (dir == 1 ? c.Xmax : ptrdiff_t(c.Xmax) * c.Ymax);
+	double epsilon[XO_MAXS + 2];
+	epsilon[0] = 1.0e-13, epsilon[1] = 1.0e-13;
+	for (int ii = 2; ii < c.NS + 2; ii++)
+		epsilon[ii] = 0.0;
+	for (int k = c.Bw_Z; k < c.Zmax - c.Bw_Z; k++)
+		for (int j = c.Bw_Y; j < c.Ymax - c.Bw_Y; j++)
+			for (int i = c.Bw_X; i < c.Xmax - c.Bw_X; i++)
+			{
+				size_t id_l = XO_ID(i, j, k) * E, id_r = (XO_ID(i, j, k) + st) * E;
+				double rho_min, theta, theta_u, theta_p, F_LF[XO_MAXE], FF_LF[XO_MAXE], FF[XO_MAXE];
+				const double *UU = &(UI[id_l]), *UP = &(UI[id_r]);
+				for (int n = 0; n < E; n++)
+				{
+					F_LF[n] = 0.5 * (Fl[n + id_l] + Fl[n + id_r] + lambda_0 * (UI[n + id_l] - UI[n + id_r]));
+					FF_LF[n] = 2.0 * lambda * F_LF[n];
+					FF[n] = 2.0 * lambda * Fwall[n + id_l];
+				}
+				theta_u = 1.0, theta_p = 1.0;
+				rho_min = std::fmin(UU[0], epsilon[0]);
+				if (UU[0] - FF[0] < rho_min)
+					theta_u = (UU[0] - FF_LF[0] - rho_min + 1.0e-40) / (FF[0] - FF_LF[0] + 1.0e-40);
+				rho_min = std::fmin(UP[0], epsilon[0]);
+				if (UP[0] + FF[0] < rho_min)
+					theta_p = (UP[0] + FF_LF[0] - rho_min + 1.0e-40) / (FF_LF[0] - FF[0] + 1.0e-40);
+				theta = std::fmin(std::fmax(std::fmin(theta_u, theta_p), 0.0), 1.0);
+				for (int n = 0; n < E; n++)
+				{
+					FF[n] = (1.0 - theta) * FF_LF[n] + theta * FF[n];
+					Fwall[n + id_l] = (1.0 - theta) * F_LF[n] + theta * Fwall[n + id_l];
+				}
+				double yi_q[XO_MAXS], yi_u[XO_MAXS], yi_qp[XO_MAXS], yi_up[XO_MAXS], _rhoq, _rhou, _rhoqp, _rhoup;
+				_rhoq = 1.0 / (UU[0] - FF[0]), _rhou = 1.0 / (UU[0] - FF_LF[0]);
+				_rhoqp = 1.0 / (UP[0] + FF[0]), _rhoup = 1.0 / (UP[0] + FF_LF[0]);
+				yi_q[NUM_COP] = 1.0, yi_u[NUM_COP] = 1.0, yi_qp[NUM_COP] = 1.0, yi_up[NUM_COP] = 1.0;
+				for (int n = 0; n < NUM_COP; n++)
+				{
+					int tid = n + 5;
+					yi_q[n] = (UU[tid] - FF[tid]) * _rhoq, yi_q[NUM_COP] -= yi_q[n];
+					yi_u[n] = (UU[tid] - FF_LF[tid]) * _rhou, yi_u[NUM_COP] -= yi_u[n];
+					yi_qp[n] = (UP[tid] + FF[tid]) * _rhoqp, yi_qp[NUM_COP] -= yi_qp[n];
+					yi_up[n] = (UP[tid] + FF_LF[tid]) * _rhoup, yi_up[NUM_COP] -= yi_up[n];
+					theta_u = 1.0, theta_p = 1.0;
+					double temp = epsilon[n + 2];
+					if (yi_q[n] < temp)
+					{
+						double yi_min = std::fmin(yi_u[n], temp);
+						theta_u = (yi_u[n] - yi_min + 1.0e-40) / (yi_u[n] - yi_q[n] + 1.0e-40);
+					}
+					if (yi_qp[n] < temp)
+					{
+						double yi_min = std::fmin(yi_up[n], temp);
+						theta_p = (yi_up[n] - yi_min + 1.0e-40) / (yi_up[n] - yi_qp[n] + 1.0e-40);
+					}
+					theta = std::fmin(std::fmax(std::fmin(theta_u, theta_p), 0.0), 1.0);
+					for (int nn = 0; nn < E; nn++)
+					{
+						FF[n] = (1.0 - theta) * FF_LF[n] + theta * FF[n];
+						Fwall[nn + id_l] = (1.0 - theta) * F_LF[nn] + theta * Fwall[nn + id_l];
+					}
 				}
 			}
 }
@@ -803,6 +928,16 @@ static void GetLU(const xo_cfg &c, xo_state &s, const double *UI)
 		ReconstructFlux(c, s, 1, UI, s.FluxG, s.FluxGw, s.eig_y, s.eigen_block_y);
 	if (c.DimZ)
 		ReconstructFlux(c, s, 2, UI, s.FluxH, s.FluxHw, s.eig_z, s.eigen_block_z);
+	if (c.positivity)
+	{ // ConVenction_block.hpp:330-410: lambda_d0 = uvw_c_max[d] of the last GetDt, lambda_d = CFL / lambda_d0
+		const double lx0 = s.uvw_c_max[0], ly0 = s.uvw_c_max[1], lz0 = s.uvw_c_max[2];
+		if (c.DimX)
+			PositivityPreserving(c, 0, UI, s.FluxF, s.FluxFw, lx0, c.CFL / lx0);
+		if (c.DimY)
+			PositivityPreserving(c, 1, UI, s.FluxG, s.FluxGw, ly0, c.CFL / ly0);
+		if (c.DimZ)
+			PositivityPreserving(c, 2, UI, s.FluxH, s.FluxHw, lz0, c.CFL / lz0);
+	}
 	UpdateFluidLU(c, s);
 }
 

@@ -19,7 +19,22 @@ VARIANTS = [("shock-tube", 5), ("shock-tube", 7), ("vortex", 5), ("riemann", 5),
 # exercise that driver-state semantic): tests/golden/<case>_w5_<alpha>.npz
 ALPHA_VARIANTS = [("vortex", 5, 3), ("vortex", 5, 1), ("sbi", 5, 3), ("sbi", 5, 1)]
 
+# (f) rows: WENO-CU6 (SCHEME_ORDER 6) and the positivity-preserving flux limiter (oracle/cases/<case>_pp.json: PP on, CFL 0.9 --
+# at that CFL the limiter acts from the first step on): tests/golden/<case>_w<weno>[_pp].npz
+NEXT_VARIANTS = [("sbi", 6, 0), ("shock-tube", 6, 0), ("jet", 6, 0), ("sbi", 5, 1), ("sbi", 6, 1), ("shock-tube", 5, 1)]
+
 if __name__ == "__main__":
+    for case, weno, pp in NEXT_VARIANTS:
+        res = GRID[case]
+        A, meta, out = xfref.run_ref(case, res, 10, dump_steps=(1, 10), weno=weno, stage_dump=True, pp=pp)
+        assert "ORACLE_TIMING" in out and "error=0" in out, out[-2000:]
+        np.savez_compressed(os.path.join(xfref.GOLDEN, "%s_w%d%s.npz" % (case, weno, "_pp" if pp else "")), res=np.array(res), weno=weno, pp=pp,
+                            cfl=xfref.PP_CFL if pp else xfref.CASES[case]["cfl"],
+                            ic_U=A["ic_U"], ic_T=A["ic_T"], U_step1=A["U_step1"], U_step10=A["U_step10"], T_step10=A["T_step10"],
+                            s1_LU=A["s1_LU"], s1_Fwx=A["s1_Fwx"], dt=np.array(meta["dt"]))
+        print(case, weno, "pp" if pp else "", "ok", meta["dt"][:2])
+    if "--next-only" in sys.argv:
+        sys.exit(0)
     for case, weno, alpha in ALPHA_VARIANTS:
         res = GRID[case]
         A, meta, out = xfref.run_ref(case, res, 10, dump_steps=(1, 10), weno=weno, stage_dump=True, alpha=alpha)

@@ -20,7 +20,7 @@ Ru = (6.02214076e26 * 1.380649e-23) * 1.0e-3
 
 class XoCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("Xmax", "Ymax", "Zmax", "X_inner", "Y_inner", "Z_inner", "Bw_X", "Bw_Y", "Bw_Z",
-                                       "DimX", "DimY", "DimZ", "NS", "Emax", "NCOP", "cop", "ghost_species", "weno", "alpha")] + \
+                                       "DimX", "DimY", "DimZ", "NS", "Emax", "NCOP", "cop", "ghost_species", "weno", "alpha", "positivity")] + \
                [(n, C.c_double) for n in ("dx", "dy", "dz", "_dx", "_dy", "_dz", "CFL", "ncop_gamma")] + \
                [("bc", C.c_int * 6)] + [(n, C.POINTER(C.c_double)) for n in ("Hia", "Hib", "Ri", "_Wi")]
 
@@ -69,7 +69,7 @@ def read_thermal(names):
 class Oracle:
     """One oracle state (all reference arrays, AoS) for one case/grid."""
 
-    def __init__(self, case, res, weno=5, alpha=2, so=ORACLE_SO):
+    def __init__(self, case, res, weno=5, alpha=2, so=ORACLE_SO, pp=0, cfl=None):
         if not os.path.exists(so):
             subprocess.check_call([os.path.join(REPO, "oracle", "build_oracle.sh")])
         self.lib = L = C.CDLL(so)
@@ -94,6 +94,9 @@ class Oracle:
         self.names, _, _ = read_species(cs["mix"])
         self.Hia, self.Hib, self.Wi, self._Wi, self.Ri = read_thermal(self.names)
         self.cfg = cfg = make_cfg(case, res, weno, alpha)
+        cfg.positivity = int(pp)
+        if cfl is not None:
+            cfg.CFL = cfl
         for n in ("Hia", "Hib", "Ri", "_Wi"):
             setattr(cfg, n, getattr(self, n).ctypes.data_as(C.POINTER(C.c_double)))
         self.st = L.xo_state_create(C.byref(cfg))
@@ -183,22 +186,25 @@ def make_cfg(case, res, weno=5, alpha=2, mz=1):
 
 # ---- compiled reference (oracle/_ref) ---------------------------------------------------------------
 ALPHA_NAME = {1: "ROE", 2: "LLF", 3: "GLF"}
+PP_CFL = 0.9   # CFL of the positivity-preserving variants (oracle/cases/<case>_pp.json)
 
 
-def ref_dir(case, weno=5, mode="parity", alpha=2):
+def ref_dir(case, weno=5, mode="parity", alpha=2, pp=0):
     tag = "%s_w%d_%s" % (case, weno, mode)
     if alpha != 2:
         tag += "_" + ALPHA_NAME[alpha]
+    if pp:
+        tag += "_pp"
     return os.path.join(REF_DIR, tag)
 
 
-def ref_available(case, weno=5, mode="parity", alpha=2):
-    return os.path.exists(os.path.join(ref_dir(case, weno, mode, alpha), "XFLUIDS"))
+def ref_available(case, weno=5, mode="parity", alpha=2, pp=0):
+    return os.path.exists(os.path.join(ref_dir(case, weno, mode, alpha, pp), "XFLUIDS"))
 
 
-def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None, alpha=2):
+def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None, alpha=2, pp=0):
     """Run the compiled reference; returns (dict of arrays, meta dict, stdout)."""
-    d = ref_dir(case, weno, mode, alpha)
+    d = ref_dir(case, weno, mode, alpha, pp)
     out = outdir or tempfile.mkdtemp(prefix="xfref_")
     env = dict(os.environ, XF_NSTEPS=str(nsteps), XF_DUMP_DIR=out, XF_DUMP_STEPS=",".join(map(str, dump_steps)),
                XF_DUMP_STAGE="1" if stage_dump else "0", XF_DUMP_T="1" if dump_T else "0")

@@ -50,7 +50,10 @@ __device__ __forceinline__ bool xf_bad(double x) { return (x < 0) || isnan(x) ||
 //   k_prim_hard  one thread per list entry continues the same iteration to the stop criterion or the cap
 // Both end in the same epilogue.
 // ---------------------------------------------------------------------------------------------
-constexpr int XF_NEWTON_FAST = 3;
+#ifndef XF_NEWTON_FAST_
+#define XF_NEWTON_FAST_ 3
+#endif
+constexpr int XF_NEWTON_FAST = XF_NEWTON_FAST_;
 #ifndef XF_PRIM_MINB
 #define XF_PRIM_MINB 6   // resident 128-thread blocks per SM k_prim is compiled for (register cap 65536 / (128 * XF_PRIM_MINB))
 #endif
@@ -197,14 +200,19 @@ __device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
 }
 
 template <class C>
-__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0, long long lin1)
+__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0 /* first z-plane */, long long lin1)
 {
-	const long long lin = lin0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = lin < lin1 && int(lin % d.Xp) < d.Xmax;
+	// grid: x = 128-cell chunks of one z-plane, y = plane; 32-bit index arithmetic inside the plane (a 64-bit
+	// division per cell costs more instructions than the whole epilogue)
+	const unsigned q = blockIdx.x * 128u + threadIdx.x;
+	const unsigned jq = q / (unsigned)d.Xp, iq = q - jq * (unsigned)d.Xp;
+	const int kq = int(lin0) + int(blockIdx.y);
+	const bool active = q < (unsigned)d.sZ && int(iq) < d.Xmax;
 	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	(void)lin1;
 	if (active)
 	{
-		const long long id = lin;
+		const long long id = (long long)kq * d.sZ + q;
 		constexpr int NS = C::NS, NC = C::NC;
 		PrimCell<C> pc;
 		pc.rho = U[id];
@@ -258,7 +266,11 @@ __global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th
 			}
 		}
 		if (done)
-			prim_epilogue<C>(d, th, id, cell_is_inner(d, id), pc, T, hi, Cp, flags, dtm, glf);
+		{
+			const int i = int(iq), j = int(jq), k = kq;
+			const bool inner = i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
+			prim_epilogue<C>(d, th, id, inner, pc, T, hi, Cp, flags, dtm, glf);
+		}
 	}
 	prim_reduce(d, flags, dtm, glf);
 }
@@ -406,6 +418,9 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 #ifndef XF_TF_
 #define XF_TF_ 8
 #endif
+#ifndef XF_SIDE_EARLY
+#define XF_SIDE_EARLY 0 // 1: issue the face-side loads before the stencil staging (their latency overlaps the staging)
+#endif
 constexpr int XF_TX = XF_TX_; // x-sweep: faces (cells) per block
 constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
@@ -416,6 +431,7 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
 	extern __shared__ double smem[];
 	XfSide<C> sl, sr;
+	XfRoe<C> R;
 	SmemStencil<C, WENO> st;
 	long long id_l;
 	bool valid;
@@ -424,22 +440,28 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 	{
 		constexpr int ncell = XF_TX + NST - 1;
 		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
-		// linear cell range of this block inside the inner z-planes
-		const long long id0 = (long long)d.Bz * d.sZ + (long long)blockIdx.x * XF_TX;
+		// grid: x = XF_TX-cell chunks of the linear index space of one z-plane, y = inner plane (32-bit index arithmetic;
+		// stencils of valid faces never leave their row, so cells outside the plane only feed idle threads)
+		const int kpl = d.Bz + blockIdx.y;
+		const int q0 = blockIdx.x * XF_TX;
+		const long long id0 = (long long)kpl * d.sZ + q0;
+		id_l = id0 + threadIdx.x;
+		const unsigned ql = unsigned(q0) + threadIdx.x;
+		const int j = int(ql / unsigned(d.Xp)), i = int(ql - unsigned(j) * unsigned(d.Xp));
+		valid = ql < unsigned(d.sZ) && i >= d.Bx - 1 && i < d.Bx + d.Xi && j >= d.By && j < d.By + d.Yi;
+		if (XF_SIDE_EARLY && valid)
+			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + 1, sr);
 		for (int c = threadIdx.x; c < ncell; c += XF_TX)
 		{
-			const long long id = id0 - P + c;
-			const bool ok = id >= 0 && id < d.N && int(id % d.Xp) < d.Xmax;
-			stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, c);
+			const int q = q0 - P + c;
+			const bool ok = q >= 0 && q < int(d.sZ) && int(unsigned(q) % unsigned(d.Xp)) < d.Xmax;
+			stage_cell<C, DIR>(d, U, ok ? id0 - P + c : 0, ok, sU, sF, sL, ncell, c);
 		}
+		if (XF_SIDE_EARLY == 2 && valid)
+			xf_roe_state<C>(sl, sr, d.gamma0, R);
 		__syncthreads();
-		id_l = id0 + threadIdx.x;
-		const int i = int(id_l % d.Xp);
-		const long long row = id_l / d.Xp;
-		const int j = int(row % d.Ymax), k = int(row / d.Ymax);
-		valid = id_l < d.N && i >= d.Bx - 1 && i < d.Bx + d.Xi && j >= d.By && j < d.By + d.Yi && k >= d.Bz && k < d.Bz + d.Zi;
 		st.sU = sU, st.sF = sF, st.sL = sL, st.ncell = ncell, st.base = threadIdx.x, st.stride = 1;
-		if (valid)
+		if (!XF_SIDE_EARLY && valid)
 			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + 1, sr);
 	}
 	else
@@ -457,6 +479,12 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 			f0 = d.Bz - 1 + blockIdx.z * XF_TF, j = d.By + blockIdx.y, k = 0, sS = d.sZ;
 		const int nmax = DIR == 1 ? d.Ymax : d.Zmax;
 		const bool iok = i < d.Bx + d.Xi;
+		const int qf = f0 + ty; // left cell of this thread's face
+		const int qend = DIR == 1 ? d.By + d.Yi : d.Bz + d.Zi;
+		valid = iok && qf < qend;
+		id_l = DIR == 1 ? ((long long)k * d.Ymax + qf) * d.Xp + i : ((long long)qf * d.Ymax + j) * d.Xp + i;
+		if (XF_SIDE_EARLY && valid)
+			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + sS, sr);
 		for (int r = ty; r < nrow; r += XF_TF)
 		{
 			const int q = f0 - P + r; // index along the sweep of this staged row
@@ -464,19 +492,17 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 			const long long id = DIR == 1 ? ((long long)k * d.Ymax + q) * d.Xp + i : ((long long)q * d.Ymax + j) * d.Xp + i;
 			stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, r * XF_TW + tx);
 		}
+		if (XF_SIDE_EARLY == 2 && valid)
+			xf_roe_state<C>(sl, sr, d.gamma0, R);
 		__syncthreads();
-		const int qf = f0 + ty; // left cell of this thread's face
-		const int qend = DIR == 1 ? d.By + d.Yi : d.Bz + d.Zi;
-		valid = iok && qf < qend;
-		id_l = DIR == 1 ? ((long long)k * d.Ymax + qf) * d.Xp + i : ((long long)qf * d.Ymax + j) * d.Xp + i;
 		st.sU = sU, st.sF = sF, st.sL = sL, st.ncell = ncell, st.base = ty * XF_TW + tx, st.stride = XF_TW;
-		if (valid)
+		if (!XF_SIDE_EARLY && valid)
 			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + sS, sr);
 	}
 	if (!valid)
 		return;
-	XfRoe<C> R;
-	xf_roe_state<C>(sl, sr, d.gamma0, R);
+	if (XF_SIDE_EARLY != 2)
+		xf_roe_state<C>(sl, sr, d.gamma0, R);
 	double glf[3] = {d.red[XF_RED_GLF + DIR * 3 + 0], d.red[XF_RED_GLF + DIR * 3 + 1], d.red[XF_RED_GLF + DIR * 3 + 2]};
 	double F[E];
 	xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, F);
@@ -773,17 +799,16 @@ template <class C>
 static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1)
 {
 	// z-planes [k0, k1) of the block (all of it: 0, Zmax)
-	const long long lin0 = (long long)k0 * d.sZ, lin1 = (long long)k1 * d.sZ;
-	const long long nb = (lin1 - lin0 + 127) / 128;
-	if (nb <= 0)
+	if (k1 <= k0)
 		return 0;
+	const dim3 nb((unsigned)((d.sZ + 127) / 128), (unsigned)(k1 - k0));
 	if constexpr (C::COP)
 	{
 		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
 		if (e != cudaSuccess)
 			return (int)e;
 	}
-	k_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, U, flags, lin0, lin1);
+	k_prim<C><<<nb, 128, 0, s>>>(d, th, U, flags, (long long)k0, (long long)k1);
 	XF_CHECK_LAUNCH();
 	++*launches;
 	if constexpr (C::COP)
@@ -812,8 +837,8 @@ static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
 		if (!attr_done)
 			cudaFuncSetAttribute(k_sweep<C, DIR, WENO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
-		const long long ncell = (long long)d.Zi * d.sZ;
-		k_sweep<C, DIR, WENO><<<(unsigned)((ncell + XF_TX - 1) / XF_TX), XF_TX, smem, s>>>(d, U, d.Fw[0]);
+		const dim3 g((unsigned)((d.sZ + XF_TX - 1) / XF_TX), (unsigned)d.Zi);
+		k_sweep<C, DIR, WENO><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0]);
 	}
 	else
 	{
