@@ -44,7 +44,8 @@ WORKLOADS = {
 def sweep_flops_per_face(E, NS, cop, weno=5):
     NC = NS - 1 if cop else 0
     B = 175 * NS + 40 * NC + 115 if cop else 4
-    return 32 + B + E * (34 * E + 2 * NC + (399 if weno == 7 else 212)) + 6 * E
+    # per field: split + both reconstructions: WENO5-JS 212, WENO7-JS 399, WENO-CU6 358 (counted from WENO6s_schemes.hpp:5-78)
+    return 32 + B + E * (34 * E + 2 * NC + {5: 212, 6: 358, 7: 399}[weno]) + 6 * E
 
 
 def sweep_bytes_per_cell(E):
@@ -178,7 +179,8 @@ def main():
     ap.add_argument("--grid", default=None, help="nx,ny,nz inner cells (per GPU when weak, of the whole box when strong; default: the workload's BASELINE size)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: weak for sbi (z extent grows with N), strong for jet (fixed box cut in z)")
     ap.add_argument("--fp", type=int, default=0, help="0 strict (parity mode, default), 1 FMA contraction in the sweeps")
-    ap.add_argument("--weno", type=int, default=5)
+    ap.add_argument("--weno", type=int, default=5, help="5 WENO5-JS, 6 WENO-CU6, 7 WENO7-JS")
+    ap.add_argument("--pp", type=int, default=0, help="1: positivity-preserving flux limiter on (fused into the sweep tails)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-steps", type=int, default=2)
@@ -209,7 +211,7 @@ def main():
     w = WORKLOADS[args.workload]
     grid = tuple(int(x) for x in args.grid.split(",")) if args.grid else w["grid"]
     scaling = args.scaling or ("strong" if args.workload == "jet" else "weak")
-    cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=LLF", "-fp=%d" % args.fp]
+    cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=LLF", "-fp=%d" % args.fp, "-pp=%d" % args.pp]
     if world > 1:
         cli += ["-mpi=1,1,%d" % world, "-mpi-s=%s" % scaling]
     setup = host.Setup(os.path.join(REPO, "settings", w["json"]), cli, rank=rank, nranks=world)
@@ -327,8 +329,17 @@ def main():
         fl = sweep_flops_per_face(E, setup.num_species, setup.cop, args.weno) * faces      # per launch
         t_launch = prof[top] / 3.0 * 1e-3                                                  # 3 launches (stages) per step
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same command (profiles/), if the
+        # capture was taken on this workload and grid
+        traffic, traffic_src = None, None
+        tpath = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            key = "%s:%dx%dx%d:weno%d" % (args.workload, setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner, args.weno)
+            if key in tj and top in tj[key]:
+                traffic, traffic_src = tj[key][top], tj.get("source")
         roof = {"bound": "fp64", "kernel": "k_sweep<%s>" % top[-1], "achieved": fl / t_launch / 1e12, "peak": dfma, "unit": "TFLOP/s",
-                "frac": fl / t_launch / 1e12 / dfma if dfma else None, "traffic": None,
+                "frac": fl / t_launch / 1e12 / dfma if dfma else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "FP64 FMA rate measured live by xf_measure_peaks on this device (MEASURED_PEAKS.json holds no FP64 figure; nominal 37)",
                 "hbm_view": {"achieved_gbs": sweep_bytes_per_cell(E) * inner / t_launch / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650", "copy_gbs_live": copy},
@@ -346,7 +357,7 @@ def main():
     if rank == 0:
         line = {"metric": "cell-updates/sec (Mcell*stage/s)", "value": value, "unit": "Mcell*stage/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "flux_splitting": "LLF",
+                "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "positivity_preserving": bool(args.pp), "flux_splitting": "LLF",
                            "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
                            "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
                            "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % (eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9),

@@ -58,10 +58,12 @@ typedef struct xf_thermal {
 
 /* reference compile-time scheme macros (cmake/init_options.cmake) made run-time */
 typedef struct xf_scheme {
-	int weno_order;        /* SCHEME_ORDER: 5 (WENO5-JS, weno5old) or 7 (WENO7-JS) */
+	int weno_order;        /* SCHEME_ORDER: 5 (WENO5-JS, weno5old), 6 (WENO-CU6, WENO6s_schemes.hpp:5-78) or 7 (WENO7-JS) */
 	int artificial_type;   /* Artificial_type: 1 ROE, 2 LLF, 3 GLF */
 	int fp_mode;           /* 0 strict: no FMA contraction, reference summation order (parity mode);
 	                          1 fast:   FMA contraction allowed (same formulas, same order) */
+	int positivity;        /* equations.PositivityPreserving (read_json.cpp:68): the flux limiter of
+	                          PositivityPreserving_kernels.hpp:5-76, fused into the tail of each sweep */
 } xf_scheme;
 
 typedef struct xf_ctx xf_ctx;

@@ -30,16 +30,17 @@ from xfluids_b200.slab import HaloExchanger  # noqa: E402
 CASES = {"sbi": ("shock-bubble.json", (32, 16, 16), (0.1, 0.05, 0.05)), "jet": ("expanded-jet.json", (32, 16, 16), (3.0, 1.5, 1.5))}
 
 
-def setups(case, rank, world, strong):
+def setups(case, rank, world, strong, extra=()):
     js, grid, dom = CASES[case]
     path = os.path.join(REPO, "settings", js)
+    extra = list(extra)
     if strong:
         gz = grid[2] * world   # a fixed box whose z extent is cut into `world` slabs
-        one = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], gz)])
-        mine = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], gz), "-mpi=1,1,%d" % world, "-mpi-s=strong"], rank=rank, nranks=world)
+        one = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], gz)] + extra)
+        mine = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], gz), "-mpi=1,1,%d" % world, "-mpi-s=strong"] + extra, rank=rank, nranks=world)
     else:
-        one = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], grid[2] * world), "-domain=%.17g,%.17g,%.17g" % (dom[0], dom[1], dom[2] * world)])
-        mine = host.Setup(path, ["-run=%d,%d,%d" % grid, "-mpi=1,1,%d" % world, "-mpi-s=weak"], rank=rank, nranks=world)
+        one = host.Setup(path, ["-run=%d,%d,%d" % (grid[0], grid[1], grid[2] * world), "-domain=%.17g,%.17g,%.17g" % (dom[0], dom[1], dom[2] * world)] + extra)
+        mine = host.Setup(path, ["-run=%d,%d,%d" % grid, "-mpi=1,1,%d" % world, "-mpi-s=weak"] + extra, rank=rank, nranks=world)
     return one, mine
 
 
@@ -49,9 +50,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--case", default="sbi")
     ap.add_argument("--strong", action="store_true")
+    ap.add_argument("--weno", type=int, default=5)
+    ap.add_argument("--pp", type=int, default=0, help="positivity-preserving limiter on, at CFL 0.9 (where it acts)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    one, mine = setups(a.case, rank, world, a.strong)
+    one, mine = setups(a.case, rank, world, a.strong, ["-weno=%d" % a.weno] + (["-pp=1", "-cfl=0.9"] if a.pp else []))
     E, Bz = mine.Emax, mine.block.Bwidth_Z
     zi = mine.block.Z_inner
     plane = mine.block.Xmax * mine.block.Ymax * E

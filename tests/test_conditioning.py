@@ -24,7 +24,7 @@ def rel_linf_components(a, b, E):
     return np.abs(a - b).max(axis=0) / np.maximum(den, 1e-300)
 
 
-def run_pair(case, weno, nsteps):
+def run_pair(case, weno, nsteps, norm=None):
     g = np.load(os.path.join(xfref.GOLDEN, "%s_w%d.npz" % (case, weno)))
     res = tuple(int(x) for x in g["res"])
     out = []
@@ -36,7 +36,7 @@ def run_pair(case, weno, nsteps):
         assert n == nsteps
         E = o.cfg.Emax
         out.append(o.arr("U").reshape(-1, E)[xfref.inner_mask(o.cfg)].copy())
-    return rel_linf_components(out[1], out[0], E)
+    return (norm or rel_linf_components)(out[1], out[0], E)
 
 
 @pytest.mark.parametrize("case,nsteps,bound", [("shock-tube", 1, 1e-12), ("sbi", 1, 1e-12), ("jet", 1, 1e-12),
@@ -53,3 +53,14 @@ def test_jet_amplifies_one_ulp_beyond_1e9_within_100_steps():
     e = run_pair("jet", 5, 100)
     print("jet 100 steps, 1-ulp log perturbation:", e)
     assert 1e-9 < e.max() < 5e-6
+
+
+def test_jet_cu6_conditioning():
+    """jet + WENO-CU6 (less dissipative than WENO5-JS): a 1-ulp log() perturbation already exceeds the north_star one-step figure
+    (3e-9 after one step, 2.6e-7 after 10 under the plain per-variable norm).  tests/test_gpu_parity.py bounds the CUDA path by
+    this envelope for that one fixture; SBI and the shock tube with CU6 stay far inside 1e-12 / 1e-9."""
+    plain = lambda a, b, E: np.atleast_1d(xfref.rel_linf(a, b, E))
+    e1, e10 = run_pair("jet", 6, 1, plain).max(), run_pair("jet", 6, 10, plain).max()
+    print("jet CU6, 1-ulp log perturbation: step 1 %.3e, step 10 %.3e" % (e1, e10))
+    assert 1e-12 < e1 < 1e-8 and 1e-9 < e10 < 5e-6
+    assert run_pair("sbi", 6, 10, plain).max() < 1e-11 and run_pair("shock-tube", 6, 10, plain).max() < 1e-11

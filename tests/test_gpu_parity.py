@@ -279,3 +279,76 @@ def test_guards_raise_flags_like_the_reference():
     eng.L.check(eng.L.dll.xf_clear_errors(eng.ctx))
     done, t, err = eng.run(eng.bc, 3)
     assert err == 1 and done <= 3
+
+
+# ---- WENO-CU6 and the positivity-preserving flux limiter -----------------------------------------
+NEXT_VARIANTS = [("sbi", 6, 0), ("shock-tube", 6, 0), ("jet", 6, 0), ("sbi", 5, 1), ("sbi", 6, 1), ("shock-tube", 5, 1)]
+
+
+def golden_next(case, weno, pp):
+    g = np.load(os.path.join(xfref.GOLDEN, "%s_w%d%s.npz" % (case, weno, "_pp" if pp else "")))
+    return g, tuple(int(x) for x in g["res"])
+
+
+@pytest.mark.parametrize("case,weno,pp", NEXT_VARIANTS)
+def test_cu6_and_positivity_stage1_vs_oracle(case, weno, pp):
+    """Wall fluxes and LU of stage 1 (block entry points) against the oracle: WENO-CU6 body, and the limiter fused into the sweep
+    tail (PositivityPreserving_kernels.hpp:5-76; the face below the first inner cell is not limited)."""
+    import xfgpu
+    g, res = golden_next(case, weno, pp)
+    cfl = float(g["cfl"])
+    o = xfref.Oracle(case, res, weno=weno, pp=pp, cfl=cfl)
+    o.set_state(g["ic_U"], g["ic_T"]); o.startup()
+    eng = xfgpu.make_engine(case, res, weno=weno, pp=pp, cfl=cfl)
+    E = eng.E
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    dt, m = eng.get_dt()
+    dto = o.get_dt()
+    assert abs(dt - dto) <= 1e-13 * dto
+    o.boundary(0); o.update_states(0); o.get_lu(0)
+    eng.boundary(eng.U, eng.bc); eng.update_states(eng.U); eng.get_lu(eng.U)
+    cfg = o.cfg
+    mask = xfref.inner_mask(cfg)
+    for d, nm in enumerate(("FluxFw", "FluxGw", "FluxHw")):
+        if [cfg.DimX, cfg.DimY, cfg.DimZ][d]:
+            a, b = eng.wallflux(d).reshape(-1, E), o.arr(nm).reshape(-1, E)
+            w = np.abs(b).sum(axis=1) > 0
+            den = max(np.abs(b[w]).max(), 1e-300)
+            assert np.abs(a[w] - b[w]).max() / den <= 5e-11, nm
+    if pp:  # the limiter acted somewhere in this fixture (else the test proves nothing)
+        o2 = xfref.Oracle(case, res, weno=weno, pp=0, cfl=cfl)
+        o2.set_state(g["ic_U"], g["ic_T"]); o2.startup(); o2.get_dt(); o2.boundary(0); o2.update_states(0); o2.get_lu(0)
+        acted = any(not np.array_equal(o2.arr(nm), o.arr(nm)) for nm in ("FluxFw", "FluxGw", "FluxHw"))
+        if case == "sbi":
+            assert acted
+    lu, luo = eng.download(eng.LU).reshape(-1, E)[mask], o.arr("LU").reshape(-1, E)[mask]
+    assert np.abs(lu - luo).max() / max(np.abs(luo).max(), 1e-300) <= 5e-10
+
+
+@pytest.mark.parametrize("case,weno,pp", NEXT_VARIANTS)
+def test_cu6_and_positivity_steps_vs_reference_golden(case, weno, pp):
+    """1 and 10 full steps through the fused path against the unmodified reference's output (same tolerances as WENO5/7)."""
+    import xfgpu
+    g, res = golden_next(case, weno, pp)
+    eng = xfgpu.make_engine(case, res, weno=weno, pp=pp, cfl=float(g["cfl"]))
+    E = eng.E
+    mask = xfref.inner_mask(eng.cfg)
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    done, t, err = eng.run(eng.bc, 1)
+    assert (done, err) == (1, 0)
+    e1 = xfgpu.rel_linf(eng.download(eng.U).reshape(-1, E)[mask], g["U_step1"].reshape(-1, E)[mask], E)
+    done, t, err = eng.run(eng.bc, 9)
+    assert (done, err) == (9, 0)
+    e10 = xfgpu.rel_linf(eng.download(eng.U).reshape(-1, E)[mask], g["U_step10"].reshape(-1, E)[mask], E)
+    print("\n%s weno%d pp=%d: rel Linf step1 %.3e step10 %.3e  t=%.6e (ref %.6e)" % (case, weno, pp, e1, e10, t, g["dt"][:10].sum()))
+    # jet + WENO-CU6: the reference's own algorithm turns a 1-ulp log() difference into 3e-9 after ONE step and 2.6e-7 after 10 on
+    # this grid (tests/test_conditioning.py::test_jet_cu6_conditioning) -- the bound there is the conditioning envelope
+    jet6 = case == "jet" and weno == 6
+    assert e1 <= (1e-8 if jet6 else 1e-12)
+    assert e10 <= (JET_100_BOUND if jet6 else 1e-9)
+    assert abs(t - g["dt"][:10].sum()) <= (JET_100_BOUND if jet6 else 1e-12) * t
+    assert eng.error_flags()[:3] == [0, 0, 0]

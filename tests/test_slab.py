@@ -37,9 +37,9 @@ def test_exchange_protocol_gloo(world, case, strong):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,strong", [("sbi", False), ("jet", True)])
-def test_two_slabs_equal_one_block_bitwise(case, strong):
+@pytest.mark.parametrize("case,strong,weno,pp", [("sbi", False, 5, 0), ("jet", True, 5, 0), ("sbi", False, 6, 1), ("sbi", False, 7, 0)])
+def test_two_slabs_equal_one_block_bitwise(case, strong, weno, pp):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5"] + (["--strong"] if strong else []))
+    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5", "--weno", str(weno), "--pp", str(pp)] + (["--strong"] if strong else []))

@@ -7,8 +7,10 @@ import xfref
 from xfluids_b200 import Engine, XfBlock, XfScheme, XfThermal
 
 
-def make_engine(case, res, weno=5, alpha=2, fp_mode=0, device=0):
+def make_engine(case, res, weno=5, alpha=2, fp_mode=0, device=0, pp=0, cfl=None):
     cfg = xfref.make_cfg(case, res, weno, alpha)
+    if cfl is not None:
+        cfg.CFL = cfl
     cs = xfref.CASES[case]
     names, _, _ = xfref.read_species(cs["mix"])
     Hia, Hib, Wi, _Wi, Ri = xfref.read_thermal(names)
@@ -23,7 +25,7 @@ def make_engine(case, res, weno=5, alpha=2, fp_mode=0, device=0):
     t.num_species, t.cop, t.ghost_species, t.ncop_gamma = cfg.NS, cfg.cop, cfg.ghost_species, 1.4
     keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (Hia, Hib, Ri, _Wi)]
     t.Hia, t.Hib, t.Ri, t._Wi = [a.ctypes.data_as(C.POINTER(C.c_double)) for a in keep]
-    s = XfScheme(weno, alpha, fp_mode)
+    s = XfScheme(weno, alpha, fp_mode, int(pp))
     eng = Engine(b, t, s, device=device, keepalive=keep)
     eng.cfg = cfg
     eng.bc = list(cs["bc"])

@@ -28,7 +28,7 @@ class XfThermal(C.Structure):
 
 
 class XfScheme(C.Structure):
-    _fields_ = [("weno_order", C.c_int), ("artificial_type", C.c_int), ("fp_mode", C.c_int)]
+    _fields_ = [("weno_order", C.c_int), ("artificial_type", C.c_int), ("fp_mode", C.c_int), ("positivity", C.c_int)]
 
 
 _P = C.c_void_p

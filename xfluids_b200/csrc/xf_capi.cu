@@ -123,8 +123,8 @@ extern "C"
 		if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
 			return fail(XF_ERR_CUDA, "no usable CUDA device (this library has no CPU path)");
 		CU(cudaSetDevice(device));
-		if (sc->weno_order != 5 && sc->weno_order != 7)
-			return fail(XF_ERR_ARG, "weno_order must be 5 or 7");
+		if (sc->weno_order != 5 && sc->weno_order != 6 && sc->weno_order != 7)
+			return fail(XF_ERR_ARG, "weno_order must be 5 (WENO5-JS), 6 (WENO-CU6) or 7 (WENO7-JS)");
 		if (sc->artificial_type < 1 || sc->artificial_type > 3)
 			return fail(XF_ERR_ARG, "artificial_type must be 1 (ROE), 2 (LLF) or 3 (GLF)");
 		if (th->cop && (th->num_species < 2 || th->num_species > 5))
@@ -146,9 +146,10 @@ extern "C"
 		d.Xi = bl->X_inner, d.Yi = bl->Y_inner, d.Zi = bl->Z_inner;
 		d.Bx = bl->Bwidth_X, d.By = bl->Bwidth_Y, d.Bz = bl->Bwidth_Z;
 		d.DimX = bl->DimX, d.DimY = bl->DimY, d.DimZ = bl->DimZ;
-		d.weno = sc->weno_order, d.alpha = sc->artificial_type, d.ghost = c->ghost;
+		d.weno = sc->weno_order, d.alpha = sc->artificial_type, d.ghost = c->ghost, d.positivity = sc->positivity ? 1 : 0;
 		d.sY = d.Xp, d.sZ = (long long)d.Xp * d.Ymax, d.N = d.sZ * d.Zmax;
 		d._dx = bl->_dx, d._dy = bl->_dy, d._dz = bl->_dz, d.CFL = bl->CFLnumber, d.gamma0 = th->ncop_gamma;
+		d.dx = bl->dx, d.dy = bl->dy, d.dz = bl->dz;
 		// thermo tables (Thermo_device.h coefficient use; products formed exactly as the reference forms them)
 		std::memset(&c->th, 0, sizeof(XfThermo));
 		c->th.Ru = (6.02214076e26 * 1.380649e-23) * 1.0E-3; // global_setup.h:49-54
@@ -423,6 +424,8 @@ extern "C"
 		KL(c->t->dt(c->d, c->lastUI, c->stream));
 		c->launches++;
 		CU(cudaMemcpyAsync(c->h_pin, c->d.red + XF_RED_DTMAX, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		// uvw_c_max as this GetDt leaves it is what the positivity-preserving limiter of the following GetLU calls reads
+		CU(cudaMemcpyAsync(c->d.red + XF_RED_PPL, c->d.red + XF_RED_DTMAX, 3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 		const double *m = c->h_pin;
 		if (uvw_c_max)

@@ -55,7 +55,7 @@ __device__ __forceinline__ bool xf_bad(double x) { return (x < 0) || isnan(x) ||
 #endif
 constexpr int XF_NEWTON_FAST = XF_NEWTON_FAST_;
 #ifndef XF_PRIM_MINB
-#define XF_PRIM_MINB 6   // resident 128-thread blocks per SM k_prim is compiled for (register cap 65536 / (128 * XF_PRIM_MINB))
+#define XF_PRIM_MINB 5   // (measured: 5 -> 22.5 ms, 6 -> 25.2, 8 -> 23.3, 10 -> 24.3 at 512x512x256) resident 128-thread blocks per SM k_prim is compiled for (register cap 65536 / (128 * XF_PRIM_MINB))
 #endif
 
 template <class C>
@@ -202,12 +202,20 @@ __device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
 template <class C>
 __global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0 /* first z-plane */, long long lin1)
 {
+#ifdef XF_PRIM_LINEAR
+	const long long lin = lin0 * d.sZ + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned jq = unsigned((lin / d.Xp) % d.Ymax), iq = unsigned(lin % d.Xp);
+	const int kq = int(lin / d.sZ);
+	const unsigned q = unsigned(lin - (long long)kq * d.sZ);
+	const bool active = lin < lin1 * d.sZ && int(iq) < d.Xmax;
+#else
 	// grid: x = 128-cell chunks of one z-plane, y = plane; 32-bit index arithmetic inside the plane (a 64-bit
 	// division per cell costs more instructions than the whole epilogue)
 	const unsigned q = blockIdx.x * 128u + threadIdx.x;
 	const unsigned jq = q / (unsigned)d.Xp, iq = q - jq * (unsigned)d.Xp;
 	const int kq = int(lin0) + int(blockIdx.y);
 	const bool active = q < (unsigned)d.sZ && int(iq) < d.Xmax;
+#endif
 	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	(void)lin1;
 	if (active)
@@ -338,6 +346,8 @@ __global__ void k_dt_final(XfDev d, double t_end)
 		dt = t_end - t;
 	r[XF_RED_DT] = dt;
 	r[XF_RED_TIME] = t + dt;
+	// the positivity-preserving limiter of the coming stages reads uvw_c_max as this GetDt left it (ConVenction_block.hpp:332)
+	r[XF_RED_PPL + 0] = r[XF_RED_DTMAX + 0], r[XF_RED_PPL + 1] = r[XF_RED_DTMAX + 1], r[XF_RED_PPL + 2] = r[XF_RED_DTMAX + 2];
 	r[XF_RED_DTMAX + 0] = 0.0, r[XF_RED_DTMAX + 1] = 0.0, r[XF_RED_DTMAX + 2] = 0.0;
 }
 
@@ -425,7 +435,7 @@ constexpr int XF_TX = XF_TX_; // x-sweep: faces (cells) per block
 constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
-template <class C, int DIR, int WENO>
+template <class C, int DIR, int WENO, bool PP>
 __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
 {
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
@@ -505,7 +515,18 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 		xf_roe_state<C>(sl, sr, d.gamma0, R);
 	double glf[3] = {d.red[XF_RED_GLF + DIR * 3 + 0], d.red[XF_RED_GLF + DIR * 3 + 1], d.red[XF_RED_GLF + DIR * 3 + 2]};
 	double F[E];
-	xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, F);
+	xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, DIR == 0 ? d.dx : (DIR == 1 ? d.dy : d.dz), F);
+	if constexpr (PP)
+	{ // (a template parameter: as a run-time branch the limiter cost the unlimited sweeps 2-4 %)  PositivityPreservingKernel runs over the inner cells (ConVenction_block.hpp:330-410): the face below the first inner
+	  // cell (the first face of every pencil) is never limited
+		bool lim;
+		if constexpr (DIR == 0)
+			lim = int((unsigned(blockIdx.x) * XF_TX + threadIdx.x) % unsigned(d.Xp)) >= d.Bx;
+		else
+			lim = (blockIdx.y * (DIR == 1 ? XF_TF : 0) + blockIdx.z * (DIR == 2 ? XF_TF : 0) + threadIdx.x / XF_TW) > 0;
+		if (lim)
+			xf_positivity<C, WENO>(st, d.red[XF_RED_PPL + DIR], d.CFL, F);
+	}
 #pragma unroll
 	for (int n = 0; n < E; n++)
 		Fw[n * d.N + id_l] = F[n];
@@ -801,7 +822,11 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 	// z-planes [k0, k1) of the block (all of it: 0, Zmax)
 	if (k1 <= k0)
 		return 0;
+#ifdef XF_PRIM_LINEAR
+	const dim3 nb((unsigned)((d.sZ * (k1 - k0) + 127) / 128), 1);
+#else
 	const dim3 nb((unsigned)((d.sZ + 127) / 128), (unsigned)(k1 - k0));
+#endif
 	if constexpr (C::COP)
 	{
 		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
@@ -827,8 +852,8 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 	return 0;
 }
 
-template <class C, int DIR, int WENO>
-static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
+template <class C, int DIR, int WENO, bool PP>
+static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s)
 {
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST;
 	static bool attr_done = false;
@@ -836,25 +861,30 @@ static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
 	{
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
 		if (!attr_done)
-			cudaFuncSetAttribute(k_sweep<C, DIR, WENO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
 		const dim3 g((unsigned)((d.sZ + XF_TX - 1) / XF_TX), (unsigned)d.Zi);
-		k_sweep<C, DIR, WENO><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0]);
+		k_sweep<C, DIR, WENO, PP><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0]);
 	}
 	else
 	{
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TF + NST - 1) * XF_TW * sizeof(double);
 		if (!attr_done)
-			cudaFuncSetAttribute(k_sweep<C, DIR, WENO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
 		dim3 g;
 		g.x = (d.Xi + XF_TW - 1) / XF_TW;
 		if (DIR == 1)
 			g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = d.Zi;
 		else
 			g.y = d.Yi, g.z = (d.Zi + 1 + XF_TF - 1) / XF_TF;
-		k_sweep<C, DIR, WENO><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR]);
+		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR]);
 	}
 	XF_CHECK_LAUNCH();
 	return 0;
+}
+template <class C, int DIR, int WENO>
+static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
+{
+	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s) : sweep_pp_t<C, DIR, WENO, false>(d, U, s);
 }
 template <class C>
 static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask)
@@ -866,6 +896,12 @@ static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *
 		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s), ++*launches;
 		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s), ++*launches;
 		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s), ++*launches;
+	}
+	else if (d.weno == 6)
+	{
+		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s), ++*launches;
 	}
 	else
 	{

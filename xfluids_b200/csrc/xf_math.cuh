@@ -14,6 +14,9 @@
 #include "xf_types.h"
 
 #define XF_DEV __device__ __forceinline__
+#if !defined(XF_THERMO_STATIC) && !defined(XF_THERMO_DYN)
+#define XF_THERMO_DYN // NASA-9 range as a run-time constant-bank index (one code copy, 94 registers, no spills); XF_THERMO_STATIC: 3 copies
+#endif
 
 template <int NS_, bool COP_>
 struct XfCfg
@@ -37,13 +40,34 @@ XF_DEV double xf_cp_r(const XfThermo &th, int n, double T, double _T)
 	const double *a = th.ccoef[R][n];
 	return th.Ri[n] * ((a[0] * _T + a[1]) * _T + a[2] + (a[3] + (a[4] + (a[5] + a[6] * T) * T) * T) * T);
 }
+// a / b given y = RN(1 / b): q0 = RN(a y), r = a - b q0 (exact in one fma), q = RN(q0 + r y) is the correctly rounded quotient
+// (Markstein's theorem: y within 1/2 ulp of 1/b, q0 within 1 ulp of a/b; no over/underflow for NASA-9 coefficients over 200 K <= b),
+// i.e. bit-identical to the IEEE division the reference performs -- the NS species of one evaluation share the reciprocal of T
+// instead of running NS full division sequences.  (tools/check_shared_reciprocal.c: 3e8 random pairs, 0 mismatches.)
+XF_DEV double xf_div_shared(double a, double b, double y)
+{
+#ifdef XF_NO_DIVSHARED
+	return a / b;
+#else
+	const double q0 = a * y;
+	const double r = fma(-q0, b, a);
+	return fma(r, y, q0);
+#endif
+}
 template <int R>
-XF_DEV double xf_h_r(const XfThermo &th, int n, double T, double lnT)
+XF_DEV double xf_h_r(const XfThermo &th, int n, double T, double _T, double lnT)
 {
 	const double *h = th.hcoef[R][n];
-	return th.Ri[n] * (h[0] / T + h[1] * lnT + (h[2] + (h[3] + (h[4] + (h[5] + h[6] * T) * T) * T) * T) * T + h[7]);
+	return th.Ri[n] * (xf_div_shared(h[0], T, _T) + h[1] * lnT + (h[2] + (h[3] + (h[4] + (h[5] + h[6] * T) * T) * T) * T) * T + h[7]);
 }
 XF_DEV int xf_range(double T) { return (T >= 1000.0 && T < 6000.0) ? 1 : ((T < 1000.0) ? 0 : 2); }
+// the same polynomials with the temperature range as a run-time index into the constant-bank tables: one copy of the code
+// instead of three (XF_THERMO_DYN)
+XF_DEV double xf_cp_dyn(const XfThermo &th, int r, int n, double T, double _T)
+{
+	const double *a = th.ccoef[r][n];
+	return th.Ri[n] * ((a[0] * _T + a[1]) * _T + a[2] + (a[3] + (a[4] + (a[5] + a[6] * T) * T) * T) * T);
+}
 
 // mixture Cp at T0 (get_CopCp, Mixing_device.h:61-68)
 template <class C>
@@ -52,6 +76,12 @@ XF_DEV double xf_mix_cp(const XfThermo &th, const double *yi, double T0)
 	const double T = xf_max(T0, 200.0), _T = 1.0 / T;
 	const int r = xf_range(T);
 	double cp = 0.0;
+#ifdef XF_THERMO_DYN
+#pragma unroll
+	for (int n = 0; n < C::NS; n++)
+		cp += yi[n] * xf_cp_dyn(th, r, n, T, _T);
+	return cp;
+#endif
 	if (r == 0)
 	{
 #pragma unroll
@@ -76,26 +106,35 @@ XF_DEV double xf_mix_cp(const XfThermo &th, const double *yi, double T0)
 template <class C>
 XF_DEV void xf_species_h(const XfThermo &th, double T0, double *hi)
 {
-	const double T = xf_max(T0, 200.0), lnT = log(T);
+	const double T = xf_max(T0, 200.0), lnT = log(T), _T = 1.0 / T;
 	const int r = xf_range(T);
+#ifdef XF_THERMO_DYN
+#pragma unroll
+	for (int n = 0; n < C::NS; n++)
+	{
+		const double *h = th.hcoef[r][n];
+		hi[n] = th.Ri[n] * (xf_div_shared(h[0], T, _T) + h[1] * lnT + (h[2] + (h[3] + (h[4] + (h[5] + h[6] * T) * T) * T) * T) * T + h[7]);
+	}
+#else
 	if (r == 0)
 	{
 #pragma unroll
 		for (int n = 0; n < C::NS; n++)
-			hi[n] = xf_h_r<0>(th, n, T, lnT);
+			hi[n] = xf_h_r<0>(th, n, T, _T, lnT);
 	}
 	else if (r == 1)
 	{
 #pragma unroll
 		for (int n = 0; n < C::NS; n++)
-			hi[n] = xf_h_r<1>(th, n, T, lnT);
+			hi[n] = xf_h_r<1>(th, n, T, _T, lnT);
 	}
 	else
 	{
 #pragma unroll
 		for (int n = 0; n < C::NS; n++)
-			hi[n] = xf_h_r<2>(th, n, T, lnT);
+			hi[n] = xf_h_r<2>(th, n, T, _T, lnT);
 	}
+#endif
 	if (T0 < 200.0)
 	{
 #pragma unroll
@@ -161,6 +200,45 @@ XF_DEV double xf_weno5_body(double v1, double v2, double v3, double v4, double v
 	s3 = a3 * (fma(2.0, v3, 5.0 * v4) - v5);              // 2.0 * v3 + 5.0 * v4 - v5
 	return (s1 + s2 + s3);
 }
+// WENO-CU6 (WENOCU6_BODYGPU, WENO6s_schemes.hpp:5-50; constants Utils_schemes.hpp:5-15, global_setup.h:36-37), expression order
+// as written.  The same exact-product fusions as in xf_weno5_body ( *2, *4 ).
+XF_DEV double xf_wenocu6_body(double v1, double v2, double v3, double v4, double v5, double v6, double epsilon)
+{
+	const double _six = 1.0 / 6.0, _sxtn = 1.0 / 16.0, _twfr = 1.0 / 24.0, _ohtz = 1.0 / 120.0, _ohff = 1.0 / 144.0, _ftss = 1.0 / 5760.0;
+	const double a2a2 = 13.0 / 3.0, a3a3 = 3129.0 / 80.0, a4a4 = 87617.0 / 140.0, a3a5 = 14127.0 / 224.0, a5a5 = 252337135.0 / 16128.0;
+	const double s11 = fma(-2.0, v2, v1) + v3;
+	const double s12 = fma(-4.0, v2, v1) + 3.0 * v3;
+	const double s1 = 13.0 * s11 * s11 + 3.0 * s12 * s12;
+	const double s21 = fma(-2.0, v3, v2) + v4;
+	const double s22 = v2 - v4;
+	const double s2 = 13.0 * s21 * s21 + 3.0 * s22 * s22;
+	const double s31 = fma(-2.0, v4, v3) + v5;
+	const double s32 = fma(-4.0, v4, 3.0 * v3) + v5;
+	const double s3 = 13.0 * s31 * s31 + 3.0 * s32 * s32;
+	const double tau61 = (259.0 * v6 - 1895.0 * v5 + 6670.0 * v4 - 2590.0 * v3 - 2785.0 * v2 + 341.0 * v1) * _ftss;
+	const double tau62 = -(v5 - 12.0 * v4 + 22.0 * v3 - 12.0 * v2 + v1) * _sxtn;
+	const double tau63 = -(7.0 * v6 - 47.0 * v5 + 94.0 * v4 - 70.0 * v3 + 11.0 * v2 + 5.0 * v1) * _ohff;
+	const double tau64 = (fma(-4.0, v2, fma(-4.0, v4, v5) + 6.0 * v3) + v1) * _twfr;           // v5 - 4 v4 + 6 v3 - 4 v2 + v1
+	const double tau65 = -(-v6 + 5.0 * v5 - 10.0 * v4 + 10.0 * v3 - 5.0 * v2 + v1) * _ohtz;
+	// a1a1 = 1 (exact, skipped), a1a3 = 0.5, a2a4 = 4.2, a1a5 = 0.125
+	const double s6 = (tau61 * tau61 + tau62 * tau62 * a2a2 + tau61 * tau63 * 0.5 + tau63 * tau63 * a3a3 + tau62 * tau64 * 4.2 + tau61 * tau65 * 0.125 +
+					   tau64 * tau64 * a4a4 + tau63 * tau65 * a3a5 + tau65 * tau65 * a5a5) * 12.0;
+	const double s55 = (s1 + s3 + 4.0 * s2) * _six;
+	const double s5 = fabs(s6 - s55);
+	const double r1 = 20.0 + s5 / (s1 + epsilon);
+	const double r2 = 20.0 + s5 / (s2 + epsilon);
+	const double r3 = 20.0 + s5 / (s3 + epsilon);
+	const double r4 = 20.0 + s5 / (s6 + epsilon);
+	const double a1 = 0.05 * r1, a2 = 0.45 * r2, a3 = 0.45 * r3, a4 = 0.05 * r4;
+	const double tw1 = 1.0 / (a1 + a2 + a3 + a4);
+	const double w1 = a1 * tw1, w2 = a2 * tw1, w3 = a3 * tw1, w4 = a4 * tw1;
+	double temp = 0.0;
+	temp += w1 * (fma(2.0, v1, -(7.0 * v2)) + 11.0 * v3);   // 2 v1 - 7 v2 + 11 v3
+	temp += w2 * fma(2.0, v4, 5.0 * v3 - v2);                // -v2 + 5 v3 + 2 v4
+	temp += w3 * (fma(2.0, v3, 5.0 * v4) - v5);              // 2 v3 + 5 v4 - v5
+	temp += w4 * fma(2.0, v6, 11.0 * v4 - 7.0 * v5);         // 11 v4 - 7 v5 + 2 v6
+	return temp;
+}
 XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v5, double v6, double v7)
 {
 	const double ep = 1.0e-7;
@@ -210,6 +288,16 @@ static __device__ __noinline__ double xf_split_weno5(double av, double u0, doubl
 	const double p1 = h0 + a0, p2 = h1 + a1, p3 = h2 + a2, p4 = h3 + a3, p5 = h4 + a4;
 	const double m1 = h5 - a5, m2 = h4 - a4, m3 = h3 - a3, m4 = h2 - a2, m5 = h1 - a1;
 	return (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
+}
+// WENOCU6_GPU(&pp[3], &mm[3], dl) (WENO6s_schemes.hpp:53-78): plus side cells i-2..i+3, minus side i+3..i-2; epsilon = 1e-8 dl dl
+static __device__ __noinline__ double xf_split_wenocu6(double av, double u0, double u1, double u2, double u3, double u4, double u5,
+													   double f0, double f1, double f2, double f3, double f4, double f5, double epsilon)
+{
+	const double hv = 0.5 * av;
+	const double a0 = hv * u0, a1 = hv * u1, a2 = hv * u2, a3 = hv * u3, a4 = hv * u4, a5 = hv * u5;
+	const double h0 = 0.5 * f0, h1 = 0.5 * f1, h2 = 0.5 * f2, h3 = 0.5 * f3, h4 = 0.5 * f4, h5 = 0.5 * f5;
+	return (xf_wenocu6_body(h0 + a0, h1 + a1, h2 + a2, h3 + a3, h4 + a4, h5 + a5, epsilon) +
+			xf_wenocu6_body(h5 - a5, h4 - a4, h3 - a3, h2 - a2, h1 - a1, h0 - a0, epsilon)) * (1.0 / 6.0);
 }
 static __device__ __noinline__ double xf_split_weno7(double av, double u0, double u1, double u2, double u3, double u4, double u5, double u6, double u7,
 											  double f0, double f1, double f2, double f3, double f4, double f5, double f6, double f7)
@@ -334,11 +422,11 @@ template <int WENO>
 struct XfStencil
 {
 	static constexpr int P = WENO == 7 ? 3 : 2;    // cells left of the face's left cell
-	static constexpr int NST = WENO == 7 ? 8 : 6;  // cells actually used by the reconstruction
+	static constexpr int NST = WENO == 7 ? 8 : 6;  // cells actually used by the reconstruction (WENO5-JS and WENO-CU6: i-2..i+3)
 };
 
 template <class C, int DIR, int WENO, class ST>
-XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const double *glf /*3*/, double *Fw /*E*/)
+XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const double *glf /*3*/, double dl, double *Fw /*E*/)
 {
 	constexpr int E = C::E, NC = C::NC, NST = XfStencil<WENO>::NST;
 	constexpr int ENT = DIR + 1; // row/column index of the entropy wave: x 1, y 2, z 3
@@ -466,6 +554,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 		// ---- Lax-Friedrichs splitting + WENO (one out-of-line copy: keeps the kernel inside the instruction cache) ----
 		if constexpr (WENO == 7)
 			f[n] = xf_split_weno7(av, uf[0], uf[1], uf[2], uf[3], uf[4], uf[5], uf[6], uf[7], ff[0], ff[1], ff[2], ff[3], ff[4], ff[5], ff[6], ff[7]);
+		else if constexpr (WENO == 6)
+			f[n] = xf_split_wenocu6(av, uf[0], uf[1], uf[2], uf[3], uf[4], uf[5], ff[0], ff[1], ff[2], ff[3], ff[4], ff[5], 1.e-8 * dl * dl);
 		else
 			f[n] = xf_split_weno5(av, uf[0], uf[1], uf[2], uf[3], uf[4], uf[5], ff[0], ff[1], ff[2], ff[3], ff[4], ff[5]);
 		// compiler fence: forbid keeping stencil values loaded for this field alive into the next one
@@ -525,6 +615,75 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 			const int s = (n - 4) < NC ? (n - 4) : 0;
 			Fw[4] = Fw[4] + fn * R.z[s];
 			Fw[n + 1] = Fw[n + 1] + fn;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Positivity-preserving flux limiter (PositivityPreservingKernel, PositivityPreserving_kernels.hpp:5-76) applied to the
+// wall flux this thread has just formed, from the staged conserved variables / physical fluxes of the face's two cells
+// (stencil slots P and P+1).  lambda_0 = uvw_c_max[dir] of the last GetDt, lambda = CFL / lambda_0.  epsilon = {1e-13 (rho),
+// 1e-13, 0 (every Y_i)} (ConVenction_block.hpp:334-338).  The `FF[n] = ...` statement inside the reference's species loop
+// (line 71) only rewrites entries that are never read again; it is dead and omitted.
+// ------------------------------------------------------------------------------------------------
+template <class C, int WENO, class ST>
+XF_DEV void xf_positivity(const ST &st, double lambda_0, double CFL, double *Fw /*E, in/out*/)
+{
+	constexpr int E = C::E, NC = C::NC, P = XfStencil<WENO>::P;
+	const double lambda = CFL / lambda_0;
+	const double tl = 2.0 * lambda;
+	double F_LF[E];
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		F_LF[n] = 0.5 * (st.F(P, n) + st.F(P + 1, n) + lambda_0 * (st.U(P, n) - st.U(P + 1, n)));
+	const double UU0 = st.U(P, 0), UP0 = st.U(P + 1, 0);
+	const double FF_LF0 = tl * F_LF[0];
+	double FF0 = tl * Fw[0];
+	double theta_u = 1.0, theta_p = 1.0;
+	double rho_min = xf_min(UU0, 1.0e-13);
+	if (UU0 - FF0 < rho_min)
+		theta_u = (UU0 - FF_LF0 - rho_min + 1.0e-40) / (FF0 - FF_LF0 + 1.0e-40);
+	rho_min = xf_min(UP0, 1.0e-13);
+	if (UP0 + FF0 < rho_min)
+		theta_p = (UP0 + FF_LF0 - rho_min + 1.0e-40) / (FF_LF0 - FF0 + 1.0e-40);
+	double theta = xf_min(xf_max(xf_min(theta_u, theta_p), 0.0), 1.0);
+	// FF of the species rows, limited with the density theta (the only FF entries read below)
+	double FFs[NC > 0 ? NC : 1], FF_LFs[NC > 0 ? NC : 1];
+#pragma unroll
+	for (int n = 0; n < NC; n++)
+	{
+		FF_LFs[n] = tl * F_LF[5 + n];
+		FFs[n] = (1.0 - theta) * FF_LFs[n] + theta * (tl * Fw[5 + n]);
+	}
+	FF0 = (1.0 - theta) * FF_LF0 + theta * FF0;
+#pragma unroll
+	for (int n = 0; n < E; n++)
+		Fw[n] = (1.0 - theta) * F_LF[n] + theta * Fw[n];
+	if constexpr (NC > 0)
+	{
+		const double _rhoq = 1.0 / (UU0 - FF0), _rhou = 1.0 / (UU0 - FF_LF0);
+		const double _rhoqp = 1.0 / (UP0 + FF0), _rhoup = 1.0 / (UP0 + FF_LF0);
+#pragma unroll
+		for (int n = 0; n < NC; n++)
+		{
+			const double Us = st.U(P, 5 + n), Ups = st.U(P + 1, 5 + n);
+			const double yi_q = (Us - FFs[n]) * _rhoq, yi_u = (Us - FF_LFs[n]) * _rhou;
+			const double yi_qp = (Ups + FFs[n]) * _rhoqp, yi_up = (Ups + FF_LFs[n]) * _rhoup;
+			theta_u = 1.0, theta_p = 1.0;
+			if (yi_q < 0.0)
+			{
+				const double yi_min = xf_min(yi_u, 0.0);
+				theta_u = (yi_u - yi_min + 1.0e-40) / (yi_u - yi_q + 1.0e-40);
+			}
+			if (yi_qp < 0.0)
+			{
+				const double yi_min = xf_min(yi_up, 0.0);
+				theta_p = (yi_up - yi_min + 1.0e-40) / (yi_up - yi_qp + 1.0e-40);
+			}
+			theta = xf_min(xf_max(xf_min(theta_u, theta_p), 0.0), 1.0);
+#pragma unroll
+			for (int nn = 0; nn < E; nn++)
+				Fw[nn] = (1.0 - theta) * F_LF[nn] + theta * Fw[nn];
 		}
 	}
 }

@@ -10,7 +10,8 @@
 #define XF_RED_GLF 3         // [3..11] running max |lambda|: dir*3 + {u-c, u, u+c}       (ConVenction_block.hpp:115-170)
 #define XF_RED_DT 12         // device-resident dt
 #define XF_RED_TIME 13       // device-resident physical time
-#define XF_RED_COUNT 16
+#define XF_RED_PPL 16        // [16..18] uvw_c_max of the last GetDt, kept for the positivity-preserving limiter
+#define XF_RED_COUNT 20
 
 struct XfDev
 {
@@ -18,9 +19,11 @@ struct XfDev
 	int Xi, Yi, Zi, Bx, By, Bz;        // inner sizes, ghost widths
 	int DimX, DimY, DimZ;
 	int weno, alpha, ghost;            // scheme + GhostSpecies
+	int positivity;                    // equations.PositivityPreserving (read_json.cpp:68)
 	long long N;                       // field stride = Xp*Ymax*Zmax (doubles between components)
 	long long sY, sZ;                  // cell strides along y and z
 	double _dx, _dy, _dz, CFL, gamma0;
+	double dx, dy, dz;                 // mesh widths (WENO-CU6 epsilon = 1e-8 dl dl)
 	// scalar work arrays [N] (reference FlowData, global_setup.h:218-250) + per-cell pieces of the
 	// Roe-averaged pressure derivatives (Utils_device.hpp:14-35), which are pure functions of one cell
 	double *u, *v, *w, *p, *H, *c, *T, *g3, *dpdrho, *e, *prho;

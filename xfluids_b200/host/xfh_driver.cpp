@@ -183,4 +183,31 @@ namespace xfh
 		fout.write((const char *)&el, sizeof(el));
 		fout.write((const char *)U.data(), U.size() * sizeof(double));
 	}
+
+	// XFLUIDS::Read_Ubak (XFLUIDS.cpp:689-724), called by the reference from InitialCondition (XFLUIDS.cpp:616-623): Step, Time and
+	// U replace the freshly initialised state; everything else -- notably the Newton warm-start T -- stays as the initial
+	// condition left it, exactly as in the reference.
+	bool XFLUIDS::Read_Ubak(const std::string &path)
+	{
+		std::ifstream fin(path, std::ios::binary);
+		if (!fin.is_open())
+		{
+			if (rank == 0 && verbose)
+				std::cout << "CheckingPoint-file not exist or open failed, CheckingPoint closed." << std::endl;
+			return false;
+		}
+		int Step = 0;
+		double Time = 0;
+		float el = 0;
+		std::vector<double> U(Ss.ncells() * Ss.Emax);
+		fin.read((char *)&Step, sizeof(Step));
+		fin.read((char *)&Time, sizeof(Time));
+		fin.read((char *)&el, sizeof(el));
+		fin.read((char *)U.data(), U.size() * sizeof(double));
+		if (!fin || size_t(fin.gcount()) != U.size() * sizeof(double))
+			throw std::runtime_error("CheckingPoint file " + path + " does not match this block (Xmax*Ymax*Zmax*Emax doubles expected)");
+		Iteration = Step, physicalTime = Time;
+		XFCK(xf_upload_aos(fluids[0]->ctx, fluids[0]->d_U, U.data()));
+		return true;
+	}
 } // namespace xfh

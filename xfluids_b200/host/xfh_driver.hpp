@@ -62,6 +62,7 @@ namespace xfh
 		// error flags every stage); fused = true: xf_run -- device-resident dt, one CUDA-graph replay per step.
 		bool Evolution(bool fused);
 		void Output_Ubak(const std::string &path) const;           // XFLUIDS.cpp:658-687 checkpoint format
+		bool Read_Ubak(const std::string &path);                   // XFLUIDS.cpp:689-724 restart from a checkpoint (reference or ours)
 		void DownloadU(double *h_aos) const;
 	};
 } // namespace xfh

@@ -159,6 +159,8 @@ namespace xfh
 		if (!match("-mixture").empty()) mixture = match("-mixture")[0];
 		if (!match("-weno").empty()) weno = std::atoi(match("-weno")[0].c_str());
 		if (!match("-fp").empty()) fp_mode = std::atoi(match("-fp")[0].c_str());
+		if (!match("-pp").empty()) PositivityPreserving = std::atoi(match("-pp")[0].c_str()) != 0;
+		if (!match("-cfl").empty()) bl.CFLnumber = std::atof(match("-cfl")[0].c_str());
 		if (!match("-alpha").empty())
 		{
 			const std::string a = match("-alpha")[0];

@@ -5,7 +5,7 @@
 //
 // What is compile-time in the reference (INIT_SAMPLE, MIXTURE_MODEL, WENO_ORDER, ARTIFICIAL_VISC_TYPE; cmake/*.cmake)
 // is run-time here: optional JSON section "b200" {sample, mixture, weno, artificial, fp_mode} or -sample= -mixture=
-// -weno= -alpha= -fp= on the command line.  The reference ignores unknown JSON keys, so files stay interchangeable.
+// -weno= -alpha= -fp= -pp= -cfl= on the command line (-pp overrides equations.PositivityPreserving, -cfl run.CFLnumber).  The reference ignores unknown JSON keys, so files stay interchangeable.
 #pragma once
 #include <string>
 #include <vector>
@@ -83,7 +83,7 @@ namespace xfh
 		void print() const;
 
 		xf_thermal thermal() const;
-		xf_scheme scheme() const { return xf_scheme{weno, artificial, fp_mode}; }
+		xf_scheme scheme() const { return xf_scheme{weno, artificial, fp_mode, PositivityPreserving ? 1 : 0}; }
 		size_t ncells() const { return size_t(bl.Xmax) * bl.Ymax * bl.Zmax; }
 		// neighbour-aware boundary list for this rank's slab: BC_COPY on interior z faces (mpiPacks.cpp:44-72)
 		void rank_boundarys(int out[6]) const;
