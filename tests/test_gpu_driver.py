@@ -1,0 +1,67 @@
+"""GPU (-m gpu): the `xfluids` executable (C++ host mirror of main.cpp / XFLUIDS::Evolution on the CUDA engine): checkpoint
+written in the reference's CheckingPoint layout (XFLUIDS.cpp:658-687) and restart from it (XFLUIDS.cpp:616-623, 689-724)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import xfref
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(xfref.REPO, "xfluids_b200", "xfluids")
+
+
+def read_ckpt(path, n):
+    raw = open(path, "rb").read()
+    step, = struct.unpack_from("<i", raw, 0)
+    time, = struct.unpack_from("<d", raw, 4)
+    U = np.frombuffer(raw, dtype="<f8", count=n, offset=16)
+    assert len(raw) == 16 + 8 * n
+    return step, time, U
+
+
+def run(args):
+    r = subprocess.run([EXE] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("js,grid,E,cfl_extra", [("2d-euler-vortex.json", (64, 64, 0), 5, []), ("shock-bubble.json", (24, 12, 12), 9, ["-weno=6", "-pp=1", "-cfl=0.9"])])
+def test_checkpoint_and_restart(tmp_path, js, grid, E, cfl_extra):
+    import xfgpu  # noqa: F401  (fails loudly if the CUDA library is missing)
+    from xfluids_b200 import capi, host
+    settings = os.path.join(xfref.REPO, "settings", js)
+    g = "%d,%d,%d" % grid
+    b, c = str(tmp_path / "b.ckpt"), str(tmp_path / "c.ckpt")
+    run([settings, "-run=%s,6" % g, "-ckpt=" + b, "-quiet"] + cfl_extra)
+    out = run([settings, "-run=%s,12" % g, "-restart=" + b, "-ckpt=" + c, "-quiet"] + cfl_extra)
+    assert "steps=12" in out
+    s = host.Setup(settings, ["-run=%s" % g] + cfl_extra)
+    n = s.ncells * E
+    sb, tb, Ub = read_ckpt(b, n)
+    sc, tc, Uc = read_ckpt(c, n)
+    assert (sb, sc) == (6, 12) and tc > tb > 0
+    # the same continuation through the C ABI: the reference's restart keeps everything but Step, Time and U as the initial
+    # condition left it (the Newton warm-start T in particular), then BC + UpdateStates, then the time loop
+    eng = capi.Engine(s.block, s.thermal, s.scheme, device=0, keepalive=(s,))
+    U0, T0 = s.initial_condition()
+    eng.set_state(U0, T0)                                   # U = U1 = initial condition, T = its warm start (InitialU)
+    eng.upload(eng.U, np.ascontiguousarray(Ub))            # Read_Ubak replaces d_U only: U1's never-refilled Inflow ghosts stay at the IC
+    eng.set_time(tb)
+    eng.boundary(eng.U, s.bc)
+    assert eng.update_states(eng.U) == 0
+    # XFLUIDS::Evolution: dt is clipped to every output time stamp on the way (XFLUIDS.cpp:167-199)
+    left, t = 6, tb
+    for stamp in s.stamps:
+        if left == 0:
+            break
+        if stamp <= t:
+            continue
+        done, t, err = eng.run(s.bc, left, t_end=stamp)
+        assert err == 0
+        left -= done
+    assert left == 0
+    assert t == tc
+    assert np.array_equal(eng.download(eng.U), Uc)

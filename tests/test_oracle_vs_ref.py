@@ -24,3 +24,21 @@ def test_oracle_bitexact_vs_compiled_reference(case, res, weno, nsteps):
     assert np.array_equal(np.array(dts), np.array(meta["dt"]))
     assert np.array_equal(o.arr("U"), A["U_step%d" % nsteps])
     assert np.array_equal(o.arr("T"), A["T_step%d" % nsteps])
+
+
+@pytest.mark.parametrize("case,res,weno,pp,nsteps", [("sbi", (20, 12, 8), 6, 0, 20), ("sbi", (20, 12, 8), 6, 1, 20), ("sbi", (20, 12, 8), 5, 1, 20),
+                                                     ("shock-tube", (400, 0, 0), 6, 0, 60), ("shock-tube", (400, 0, 0), 5, 1, 60), ("jet", (16, 12, 8), 6, 0, 20)])
+def test_oracle_bitexact_vs_compiled_reference_cu6_and_positivity(case, res, weno, pp, nsteps):
+    """SURVEY 8(f) rows 1-2 on grids other than the golden ones: WENO-CU6 and the positivity-preserving limiter (CFL 0.9)."""
+    if not xfref.ref_available(case, weno, pp=pp):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    A, meta, out = xfref.run_ref(case, res, nsteps, dump_steps=(nsteps,), weno=weno, stage_dump=True, pp=pp)
+    assert "error=0" in out
+    o = xfref.Oracle(case, res, weno=weno, pp=pp, cfl=xfref.PP_CFL if pp else None)
+    o.set_state(A["ic_U"], A["ic_T"])
+    o.startup()
+    n, dts, t = o.run(nsteps)
+    assert n == nsteps
+    assert np.array_equal(np.array(dts), np.array(meta["dt"]))
+    assert np.array_equal(o.arr("U"), A["U_step%d" % nsteps])
+    assert np.array_equal(o.arr("T"), A["T_step%d" % nsteps])

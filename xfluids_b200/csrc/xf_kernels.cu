@@ -353,7 +353,7 @@ __global__ void k_dt_final(XfDev d, double t_end)
 
 // ---------------------------------------------------------------------------------------------
 // k_sweep: ReconstructFlux{X,Y,Z} (Reconstruction_kernels.hpp:8-199).  One thread per face; the stencil's conserved
-// variables, physical fluxes (GetPhysFlux, Update_device.hpp:81-110) and local wave speeds are staged once per
+// variables, (halved) physical fluxes (GetPhysFlux, Update_device.hpp:81-110) and local wave speeds are staged once per
 // tile in shared memory as SoA pencils [component][cell], so a face reads its NST cells conflict-free.
 //   DIR 0: tile = 128 consecutive cells of the linear index space (rows are contiguous; non-face cells idle)
 //   DIR 1/2: tile = 32 (x) x TF faces along the sweep; staged rows = TF + NST - 1
@@ -397,9 +397,12 @@ __device__ __forceinline__ void stage_cell(const XfDev &d, const double *__restr
 #pragma unroll
 	for (int s = 0; s < NC; s++)
 		Fc[5 + s] = m * d.y[s * d.N + id];
+	// the physical flux is staged HALVED: every use below is linear in F and 0.5 * F commutes with every rounding of the projection
+	// sums, so 0.5 * (sum_k F_k l_k) == sum_k (0.5 F_k) l_k bit for bit -- one multiplication per staged cell instead of one per
+	// stencil point, field and face in the Lax-Friedrichs split
 #pragma unroll
 	for (int n = 0; n < E; n++)
-		sU[n * ncell + c] = Uc[n], sF[n * ncell + c] = Fc[n];
+		sU[n * ncell + c] = Uc[n], sF[n * ncell + c] = 0.5 * Fc[n];
 	sL[c] = fabs(un - cc), sL[ncell + c] = fabs(un), sL[2 * ncell + c] = fabs(un + cc);
 }
 
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 	SmemStencil<C, WENO> st;
 	long long id_l;
 	bool valid;
+	int sweep_tile = 0;
 
 	if constexpr (DIR == 0)
 	{
@@ -479,14 +483,19 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 		constexpr int nrow = XF_TF + NST - 1, ncell = nrow * XF_TW;
 		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
 		const int tx = threadIdx.x % XF_TW, ty = threadIdx.x / XF_TW;
-		const int i = d.Bx + blockIdx.x * XF_TW + tx;
+		// block -> (x chunk, tile along the sweep, transverse index) = blockIdx.(x, y, z) for both sweeps: blocks that share halo rows /
+		// planes run close together, so the 5 (7) halo planes of a z tile come from L2 instead of DRAM a second time (ncu: 43.9 GB
+		// read per launch with the z tile as the slowest block index, vs 30.2 GB in x / y)
+		const int bx = blockIdx.x;
+		sweep_tile = blockIdx.y;
+		const int i = d.Bx + bx * XF_TW + tx;
 		// faces along the sweep start at B-1 ; the other transverse index is inner
 		int j, k, f0;
 		long long sS; // cell stride along the sweep
 		if constexpr (DIR == 1)
-			f0 = d.By - 1 + blockIdx.y * XF_TF, k = d.Bz + blockIdx.z, j = 0, sS = d.sY;
+			f0 = d.By - 1 + sweep_tile * XF_TF, k = d.Bz + blockIdx.z, j = 0, sS = d.sY;
 		else
-			f0 = d.Bz - 1 + blockIdx.z * XF_TF, j = d.By + blockIdx.y, k = 0, sS = d.sZ;
+			f0 = d.Bz - 1 + sweep_tile * XF_TF, j = d.By + blockIdx.z, k = 0, sS = d.sZ;
 		const int nmax = DIR == 1 ? d.Ymax : d.Zmax;
 		const bool iok = i < d.Bx + d.Xi;
 		const int qf = f0 + ty; // left cell of this thread's face
@@ -523,7 +532,7 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 		if constexpr (DIR == 0)
 			lim = int((unsigned(blockIdx.x) * XF_TX + threadIdx.x) % unsigned(d.Xp)) >= d.Bx;
 		else
-			lim = (blockIdx.y * (DIR == 1 ? XF_TF : 0) + blockIdx.z * (DIR == 2 ? XF_TF : 0) + threadIdx.x / XF_TW) > 0;
+			lim = (sweep_tile * XF_TF + threadIdx.x / XF_TW) > 0;
 		if (lim)
 			xf_positivity<C, WENO>(st, d.red[XF_RED_PPL + DIR], d.CFL, F);
 	}
@@ -553,13 +562,34 @@ __device__ __forceinline__ bool inner_cell(const XfDev &d, long long &id)
 // lower z-face flux a block needs (Fw_z at k-1) was read by the block just before it and the lower y-face flux by a block
 // Zi launches earlier (~28 MB of traffic at 512^3) -- both still in L2.  With the x-fastest order of inner_cell the reuse
 // distance of Fw_z is one whole plane of every array (~120 MB) and the k-1 values come from DRAM a second time.
+#ifndef XF_RK_TILE
+#define XF_RK_TILE 8 // > 0: walk the (y, z) plane of blocks in XF_RK_TILE x XF_RK_TILE tiles (z fastest inside a tile, tiles y fastest); 0: z-fastest columns.  Measured 512x512x256: 18.0 -> 15.0 ms per step (tile 4, 8, 16 alike)
+#endif
 __device__ __forceinline__ bool inner_cell_zfast(const XfDev &d, long long &id)
 {
 	const long long b = blockIdx.x;
-	const int k = int(b % d.Zi);
-	const long long r = b / d.Zi;
-	const int j = int(r % d.Yi);
-	const int i = int(r / d.Yi) * blockDim.x + threadIdx.x;
+	int j, k, xc;
+	if (XF_RK_TILE > 0)
+	{
+		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 1;
+		const int nty = (d.Yi + TT - 1) / TT, ntz = (d.Zi + TT - 1) / TT;
+		const unsigned per_x = unsigned(nty) * unsigned(ntz) * (TT * TT);
+		xc = int(b / per_x);
+		const unsigned r = unsigned(b - (long long)xc * per_x);
+		const unsigned tile = r / (TT * TT), w = r % (TT * TT);
+		k = int(tile / nty) * TT + int(w % TT);
+		j = int(tile % nty) * TT + int(w / TT);
+		if (j >= d.Yi || k >= d.Zi)
+			return false;
+	}
+	else
+	{
+		k = int(b % d.Zi);
+		const long long r = b / d.Zi;
+		j = int(r % d.Yi);
+		xc = int(r / d.Yi);
+	}
+	const int i = xc * blockDim.x + threadIdx.x;
 	if (i >= d.Xi)
 		return false;
 	id = ((long long)(k + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
@@ -871,11 +901,10 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s)
 		if (!attr_done)
 			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
 		dim3 g;
-		g.x = (d.Xi + XF_TW - 1) / XF_TW;
 		if (DIR == 1)
-			g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = d.Zi;
+			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = d.Zi;
 		else
-			g.y = d.Yi, g.z = (d.Zi + 1 + XF_TF - 1) / XF_TF;
+			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Zi + 1 + XF_TF - 1) / XF_TF, g.z = d.Yi;
 		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR]);
 	}
 	XF_CHECK_LAUNCH();
@@ -952,7 +981,10 @@ int launch_rk(const XfDev &d, int E_, double *U, double *U1, const double *LU, d
 	const long long n = (long long)d.Xi * d.Yi * d.Zi;
 	if (fused)
 	{
-		const long long nb = (long long)((d.Xi + 255) / 256) * d.Yi * d.Zi; // one block per (x chunk, y, z), z fastest
+		long long nb = (long long)((d.Xi + 255) / 256) * d.Yi * d.Zi; // one block per (x chunk, y, z), z fastest
+		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 1;
+		if (XF_RK_TILE > 0)
+			nb = (long long)((d.Xi + 255) / 256) * ((d.Yi + TT - 1) / TT) * ((d.Zi + TT - 1) / TT) * (TT * TT);
 		XF_DISPATCH_E(E_, k_rk<E, true><<<(unsigned)nb, 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
 	}
 	else

@@ -225,10 +225,19 @@ XF_DEV double xf_wenocu6_body(double v1, double v2, double v3, double v4, double
 					   tau64 * tau64 * a4a4 + tau63 * tau65 * a3a5 + tau65 * tau65 * a5a5) * 12.0;
 	const double s55 = (s1 + s3 + 4.0 * s2) * _six;
 	const double s5 = fabs(s6 - s55);
+#ifndef XF_CU6_NOZSKIP // measured (512x256x256, SBI): 52 ms -> 33 ms per sweep direction
+	// s5 == 0 (exactly uniform stencil): 0 / (s + epsilon) = +0 for every positive denominator; skips four divisions whose zero
+	// numerator sends libdevice's division to its slow path
+	double q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
+	if (s5 != 0.0)
+		q1 = s5 / (s1 + epsilon), q2 = s5 / (s2 + epsilon), q3 = s5 / (s3 + epsilon), q4 = s5 / (s6 + epsilon);
+	const double r1 = 20.0 + q1, r2 = 20.0 + q2, r3 = 20.0 + q3, r4 = 20.0 + q4;
+#else
 	const double r1 = 20.0 + s5 / (s1 + epsilon);
 	const double r2 = 20.0 + s5 / (s2 + epsilon);
 	const double r3 = 20.0 + s5 / (s3 + epsilon);
 	const double r4 = 20.0 + s5 / (s6 + epsilon);
+#endif
 	const double a1 = 0.05 * r1, a2 = 0.45 * r2, a3 = 0.45 * r3, a4 = 0.05 * r4;
 	const double tw1 = 1.0 / (a1 + a2 + a3 + a4);
 	const double w1 = a1 * tw1, w2 = a2 * tw1, w3 = a3 * tw1, w4 = a4 * tw1;
@@ -264,7 +273,8 @@ XF_DEV double xf_weno7_body(double v1, double v2, double v3, double v4, double v
 	const double a2 = C2 / ((ep + S2) * (ep + S2));
 	const double a3 = C3 / ((ep + S3) * (ep + S3));
 	const double sum = a0 + a1 + a2 + a3;
-	const double W0 = a0 / sum, W1 = a1 / sum, W2 = a2 / sum, W3 = a3 / sum;
+	const double _sum = 1.0 / sum; // four quotients by the same denominator: one division + exact residual corrections (xf_div_shared)
+	const double W0 = xf_div_shared(a0, sum, _sum), W1 = xf_div_shared(a1, sum, _sum), W2 = xf_div_shared(a2, sum, _sum), W3 = xf_div_shared(a3, sum, _sum);
 	const double q0 = -3.0 / 12.0 * v1 + 13.0 / 12.0 * v2 - 23.0 / 12.0 * v3 + 25.0 / 12.0 * v4;
 	const double q1 = 1.0 / 12.0 * v2 - 5.0 / 12.0 * v3 + 13.0 / 12.0 * v4 + 3.0 / 12.0 * v5;
 	const double q2 = -1.0 / 12.0 * v3 + 7.0 / 12.0 * v4 + 7.0 / 12.0 * v5 - 1.0 / 12.0 * v6;
@@ -282,9 +292,10 @@ static __device__ __noinline__ double xf_split_weno5(double av, double u0, doubl
 	// stencil s=0..5 <-> cells i-2..i+3 ; weno5old_GPU(&pp[3],&mm[3]): plus uses i-2..i+2, minus i+3..i-1
 	// 0.5 * (f + av * u) == 0.5 * f + (0.5 * av) * u bit for bit (scaling by a power of two commutes with rounding), which
 	// needs one multiplication less per stencil point than halving pp and mm separately
+	// f0..f5 arrive halved (the stencil stages 0.5 * F, see stage_cell)
 	const double hv = 0.5 * av;
 	const double a0 = hv * u0, a1 = hv * u1, a2 = hv * u2, a3 = hv * u3, a4 = hv * u4, a5 = hv * u5;
-	const double h0 = 0.5 * f0, h1 = 0.5 * f1, h2 = 0.5 * f2, h3 = 0.5 * f3, h4 = 0.5 * f4, h5 = 0.5 * f5;
+	const double h0 = f0, h1 = f1, h2 = f2, h3 = f3, h4 = f4, h5 = f5;
 	const double p1 = h0 + a0, p2 = h1 + a1, p3 = h2 + a2, p4 = h3 + a3, p5 = h4 + a4;
 	const double m1 = h5 - a5, m2 = h4 - a4, m3 = h3 - a3, m4 = h2 - a2, m5 = h1 - a1;
 	return (xf_weno5_body(p1, p2, p3, p4, p5) + xf_weno5_body(m1, m2, m3, m4, m5)) * (1.0 / 6.0);
@@ -295,7 +306,7 @@ static __device__ __noinline__ double xf_split_wenocu6(double av, double u0, dou
 {
 	const double hv = 0.5 * av;
 	const double a0 = hv * u0, a1 = hv * u1, a2 = hv * u2, a3 = hv * u3, a4 = hv * u4, a5 = hv * u5;
-	const double h0 = 0.5 * f0, h1 = 0.5 * f1, h2 = 0.5 * f2, h3 = 0.5 * f3, h4 = 0.5 * f4, h5 = 0.5 * f5;
+	const double h0 = f0, h1 = f1, h2 = f2, h3 = f3, h4 = f4, h5 = f5; // halved by the staging
 	return (xf_wenocu6_body(h0 + a0, h1 + a1, h2 + a2, h3 + a3, h4 + a4, h5 + a5, epsilon) +
 			xf_wenocu6_body(h5 - a5, h4 - a4, h3 - a3, h2 - a2, h1 - a1, h0 - a0, epsilon)) * (1.0 / 6.0);
 }
@@ -304,12 +315,14 @@ static __device__ __noinline__ double xf_split_weno7(double av, double u0, doubl
 {
 	const double uf[8] = {u0, u1, u2, u3, u4, u5, u6, u7}, ff[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
 	double pp[8], mm[8];
+	// ff arrives halved: 0.5 * (ff +- av uf) == 0.5 ff +- (0.5 av) uf bit for bit (scaling by 0.5 commutes with rounding)
+	const double hv = 0.5 * av;
 #pragma unroll
 	for (int s = 0; s < 8; s++)
 	{
-		const double au = av * uf[s];
-		pp[s] = 0.5 * (ff[s] + au);
-		mm[s] = 0.5 * (ff[s] - au);
+		const double au = hv * uf[s];
+		pp[s] = ff[s] + au;
+		mm[s] = ff[s] - au;
 	}
 	// weno7_P(&pp[3]): f[-3..3]; weno7_M(&mm[3]): k=1, v1=f[4] ... v7=f[-2]
 	return xf_weno7_body(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6]) + xf_weno7_body(mm[7], mm[6], mm[5], mm[4], mm[3], mm[2], mm[1]);
@@ -414,7 +427,7 @@ XF_DEV void xf_roe_state(const XfSide<C> &l, const XfSide<C> &r, double gamma0, 
 // Characteristic-wise split flux at one face (MARCO_FLUXWALL_WENO5/7, Eigen_callback.h:127-230, with the
 // rows of L / columns of R from Eigen_matrix.hpp:7-455).
 //
-// ST is a stencil accessor: ST::U(s,n), ST::F(s,n) conserved variable / physical flux component n of
+// ST is a stencil accessor: ST::U(s,n), ST::F(s,n) conserved variable / HALF the physical flux component n of
 // stencil cell s (s = 0..NST-1 <-> offset m = s-P along the sweep), ST::lam(s,t) = |u_d - c|, |u_d|,
 // |u_d + c| (t = 0,1,2) of that cell.  Face lies between s = P and s = P+1.
 // ------------------------------------------------------------------------------------------------
@@ -635,7 +648,7 @@ XF_DEV void xf_positivity(const ST &st, double lambda_0, double CFL, double *Fw 
 	double F_LF[E];
 #pragma unroll
 	for (int n = 0; n < E; n++)
-		F_LF[n] = 0.5 * (st.F(P, n) + st.F(P + 1, n) + lambda_0 * (st.U(P, n) - st.U(P + 1, n)));
+		F_LF[n] = 0.5 * (2.0 * (st.F(P, n) + st.F(P + 1, n)) + lambda_0 * (st.U(P, n) - st.U(P + 1, n))); // st.F is 0.5 F: 2 (hFl + hFr) == Fl + Fr exactly
 	const double UU0 = st.U(P, 0), UP0 = st.U(P + 1, 0);
 	const double FF_LF0 = tl * F_LF[0];
 	double FF0 = tl * Fw[0];
