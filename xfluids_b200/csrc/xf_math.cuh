@@ -460,9 +460,80 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 	}
 
 	double f[E];
+	// The two acoustic rows (n = 0, E-1) of L differ only in their first entry and in the entry of the normal momentum: the other
+	// E - 2 products U_k l_k / F_k l_k are the same numbers in both rows (-0.5 (b1 u) == 0.5 (-b1 u) exactly), and both rows read the
+	// same stencil.  Projected together: one pass of shared-memory loads and E - 2 shared products per stencil value; each row keeps
+	// its own k-ascending summation, so every partial sum is the one the reference forms.  (Measured, 512x256x256: sweeps
+	// 19.71 / 20.57 / 20.27 -> 18.22 / 19.68 / 19.20 ms with the component-0 hoist below; also carrying the entropy row along made
+	// it slower again, 19.74 / 21.00 / 20.58 -- profiles/r01_tuning.md.)  WENO7: 32 accumulators do not fit, rows stay separate.
+	constexpr bool PAIR = (WENO != 7);
+	if constexpr (PAIR)
+	{
+		const double lA0 = 0.5 * (b2 + un_c + b3), lB0 = 0.5 * (b2 - un_c + b3);
+		double ufA[NST], ffA[NST], ufB[NST], ffB[NST];
+#pragma unroll
+		for (int s = 0; s < NST; s++)
+		{
+			const double u0 = st.U(s, 0), f0 = st.F(s, 0);
+			ufA[s] = u0 * lA0, ffA[s] = f0 * lA0, ufB[s] = u0 * lB0, ffB[s] = f0 * lB0;
+		}
+#pragma unroll
+		for (int k = 1; k < E; k++)
+		{
+			if (k == 1 + DIR)
+			{
+				const double lAn = -0.5 * (b1 * un + c1), lBn = 0.5 * (-b1 * un + c1);
+#pragma unroll
+				for (int s = 0; s < NST; s++)
+				{
+					const double uk = st.U(s, k), fk = st.F(s, k);
+					ufA[s] = ufA[s] + uk * lAn, ffA[s] = ffA[s] + fk * lAn;
+					ufB[s] = ufB[s] + uk * lBn, ffB[s] = ffB[s] + fk * lBn;
+				}
+			}
+			else
+			{
+				const double lk = (k <= 3) ? -0.5 * (b1 * (k == 1 ? R.u : (k == 2 ? R.v : R.w))) : ((k == 4) ? 0.5 * b1 : -0.5 * b1 * R.z[(k - 5) < NC ? (k - 5) : 0]);
+#pragma unroll
+				for (int s = 0; s < NST; s++)
+				{
+					const double pu = st.U(s, k) * lk, pf = st.F(s, k) * lk;
+					ufA[s] = ufA[s] + pu, ffA[s] = ffA[s] + pf;
+					ufB[s] = ufB[s] + pu, ffB[s] = ffB[s] + pf;
+				}
+			}
+		}
+		const double avA = (alpha == 1) ? fabs(un - R.c) : ((alpha == 2) ? lmax[0] : glf[0]);
+		const double avB = (alpha == 1) ? fabs(un + R.c) : ((alpha == 2) ? lmax[2] : glf[2]);
+		if constexpr (WENO == 6)
+		{
+			f[0] = xf_split_wenocu6(avA, ufA[0], ufA[1], ufA[2], ufA[3], ufA[4], ufA[5], ffA[0], ffA[1], ffA[2], ffA[3], ffA[4], ffA[5], 1.e-8 * dl * dl);
+			f[E - 1] = xf_split_wenocu6(avB, ufB[0], ufB[1], ufB[2], ufB[3], ufB[4], ufB[5], ffB[0], ffB[1], ffB[2], ffB[3], ffB[4], ffB[5], 1.e-8 * dl * dl);
+		}
+		else if constexpr (WENO == 5)
+		{
+			f[0] = xf_split_weno5(avA, ufA[0], ufA[1], ufA[2], ufA[3], ufA[4], ufA[5], ffA[0], ffA[1], ffA[2], ffA[3], ffA[4], ffA[5]);
+			f[E - 1] = xf_split_weno5(avB, ufB[0], ufB[1], ufB[2], ufB[3], ufB[4], ufB[5], ffB[0], ffB[1], ffB[2], ffB[3], ffB[4], ffB[5]);
+		}
+		asm volatile("" ::: "memory");
+	}
+	// component 0 of the stencil enters every remaining row: read it from shared memory once (WENO5 only: with the longer CU6 / WENO7
+	// bodies the 12-16 extra live doubles spill)
+	constexpr bool HOIST = (WENO == 5);
+	double U0s[NST], F0s[NST];
+	if constexpr (HOIST)
+	{
+#pragma unroll
+		for (int s = 0; s < NST; s++)
+			U0s[s] = st.U(s, 0), F0s[s] = st.F(s, 0);
+	}
+#define XF_U0(s) (HOIST ? U0s[s] : st.U(s, 0))
+#define XF_F0(s) (HOIST ? F0s[s] : st.F(s, 0))
 #pragma unroll
 	for (int n = 0; n < E; n++)
 	{
+		if (PAIR && (n == 0 || n == E - 1))
+			continue;
 		// ---- artificial viscosity for this field (Eigen_callback.h:134-145, 188-193) ----
 		const int t = (n == 0) ? 0 : ((n == E - 1) ? 2 : 1);
 		const double ev = (n == 0) ? fabs(un - R.c) : ((n == E - 1) ? fabs(un + R.c) : fabs(un));
@@ -507,8 +578,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 #pragma unroll
 			for (int s = 0; s < NST; s++)
 			{
-				uf[s] = st.U(s, 0) * l[0];
-				ff[s] = st.F(s, 0) * l[0];
+				uf[s] = XF_U0(s) * l[0];
+				ff[s] = XF_F0(s) * l[0];
 			}
 #pragma unroll
 			for (int k = 1; k < E; k++)
@@ -543,13 +614,13 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 			{
 				if (plus_unit)
 				{ // U0*(-vel) + Un
-					uf[s] = st.U(s, 0) * (-vel) + st.U(s, n);
-					ff[s] = st.F(s, 0) * (-vel) + st.F(s, n);
+					uf[s] = XF_U0(s) * (-vel) + st.U(s, n);
+					ff[s] = XF_F0(s) * (-vel) + st.F(s, n);
 				}
 				else
 				{ // U0*vel - Un
-					uf[s] = st.U(s, 0) * vel - st.U(s, n);
-					ff[s] = st.F(s, 0) * vel - st.F(s, n);
+					uf[s] = XF_U0(s) * vel - st.U(s, n);
+					ff[s] = XF_F0(s) * vel - st.F(s, n);
 				}
 			}
 		}
@@ -559,8 +630,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 #pragma unroll
 			for (int s = 0; s < NST; s++)
 			{
-				uf[s] = st.U(s, 0) * (-ys) + st.U(s, n + 1);
-				ff[s] = st.F(s, 0) * (-ys) + st.F(s, n + 1);
+				uf[s] = XF_U0(s) * (-ys) + st.U(s, n + 1);
+				ff[s] = XF_F0(s) * (-ys) + st.F(s, n + 1);
 			}
 		}
 
@@ -576,6 +647,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 		asm volatile("" ::: "memory");
 	}
 
+#undef XF_U0
+#undef XF_F0
 	// ---- back-projection Fw[k] = sum_n f[n] * R[n][k], n ascending, from 0.0 (Eigen_callback.h:222-230) ----
 #pragma unroll
 	for (int k = 0; k < E; k++)
