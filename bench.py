@@ -331,15 +331,19 @@ def main():
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same command (profiles/), if the
         # capture was taken on this workload and grid
-        traffic, traffic_src = None, None
+        traffic, traffic_src, executed = None, None, None
         tpath = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = "%s:%dx%dx%d:weno%d" % (args.workload, setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner, args.weno)
             if key in tj and top in tj[key]:
                 traffic, traffic_src = tj[key][top], tj.get("source")
+                executed = tj[key].get("executed")
         roof = {"bound": "fp64", "kernel": "k_sweep<%s>" % top[-1], "achieved": fl / t_launch / 1e12, "peak": dfma, "unit": "TFLOP/s",
                 "frac": fl / t_launch / 1e12 / dfma if dfma else None, "traffic": traffic, "traffic_source": traffic_src,
+                # `achieved` counts the reference's dense E x E arithmetic (SURVEY 8d flop model); what the kernel EXECUTES (structural
+                # zeros skipped, strict mode = no FMA contraction) and how busy the FP64 pipe is, from the committed ncu capture:
+                "executed_ncu": executed,
                 "peak_source": "FP64 FMA rate measured live by xf_measure_peaks on this device (MEASURED_PEAKS.json holds no FP64 figure; nominal 37)",
                 "hbm_view": {"achieved_gbs": sweep_bytes_per_cell(E) * inner / t_launch / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650", "copy_gbs_live": copy},
