@@ -352,3 +352,48 @@ def test_cu6_and_positivity_steps_vs_reference_golden(case, weno, pp):
     assert e10 <= (JET_100_BOUND if jet6 else 1e-9)
     assert abs(t - g["dt"][:10].sum()) <= (JET_100_BOUND if jet6 else 1e-12) * t
     assert eng.error_flags()[:3] == [0, 0, 0]
+
+
+# ---- ragged block sizes x the whole scheme matrix ------------------------------------------------------------------------------
+SETTINGS = {"shock-tube": "1d-shock-tube", "vortex": "2d-euler-vortex", "riemann": "2d-riemann", "sbi": "shock-bubble", "jet": "expanded-jet"}
+MATRIX = [  # case, inner sizes (none a multiple of a tile: x 128 / 32, y-z 8), weno, alpha, pp
+    ("sbi", (37, 19, 11), 5, 2, 0), ("sbi", (37, 19, 11), 6, 2, 1), ("sbi", (37, 19, 11), 7, 2, 1), ("sbi", (33, 9, 13), 6, 3, 0),
+    ("sbi", (33, 9, 13), 5, 1, 1), ("jet", (41, 10, 9), 7, 3, 0), ("jet", (41, 10, 9), 5, 2, 1), ("vortex", (45, 27, 0), 6, 2, 0),
+    ("vortex", (45, 27, 0), 7, 1, 1), ("riemann", (29, 131, 0), 5, 3, 1), ("shock-tube", (133, 0, 0), 6, 2, 1), ("shock-tube", (257, 0, 0), 7, 3, 0),
+]
+
+
+@pytest.mark.parametrize("case,res,weno,alpha,pp", MATRIX)
+def test_ragged_sizes_and_scheme_matrix_vs_oracle(case, res, weno, alpha, pp):
+    """Block sizes that are multiples of no tile, every reconstruction (WENO5-JS / CU6 / WENO7-JS) x splitting (ROE / LLF / GLF) x
+    limiter on/off, initial condition from the C++ host hooks: 1 and 5 steps against the CPU oracle, ghost cells included.
+    (The limiter runs at CFL 0.9, where it acts.)"""
+    import xfgpu
+    from xfluids_b200 import host
+    cfl = xfref.PP_CFL if pp else None
+    s = host.Setup(os.path.join(xfref.REPO, "settings", SETTINGS[case] + ".json"), ["-run=%d,%d,%d" % res])
+    U0, T0 = s.initial_condition()
+    o = xfref.Oracle(case, res, weno=weno, alpha=alpha, pp=pp, cfl=cfl)
+    o.set_state(U0, T0)
+    assert o.startup() == 0
+    eng = xfgpu.make_engine(case, res, weno=weno, alpha=alpha, pp=pp, cfl=cfl)
+    E = eng.E
+    eng.set_state(U0, T0)
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    errs = []
+    for nst in (1, 4):
+        n, dts, t_o = o.run(nst)
+        assert n == nst
+        done, t, err = eng.run(eng.bc, nst)
+        assert (done, err) == (nst, 0)
+        U = eng.download(eng.U)
+        if case in NOCOP:
+            assert np.array_equal(U, o.arr("U"))
+            errs.append(0.0)
+        else:
+            errs.append(xfgpu.rel_linf(U, o.arr("U"), E))
+    print("\n%s %s weno%d alpha=%d pp=%d: rel Linf (all cells) after 1 / 5 steps: %.3e / %.3e" % (case, res, weno, alpha, pp, errs[0], errs[1]))
+    jet_tol = case == "jet"  # conditioning of the jet config, see test_conditioning.py
+    assert errs[0] <= (1e-8 if jet_tol else 1e-12)
+    assert errs[1] <= (JET_100_BOUND if jet_tol else 1e-9)
