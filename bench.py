@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--host-chunks", type=int, default=None, help="z-chunks of the overlapped upload in the e2e leg (xf_set_host_overlap; 0 = plain sequence; default: the library's 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -231,6 +232,8 @@ def main():
     t_ic = time.time() - t0
 
     eng = capi.Engine(setup.block, setup.thermal, setup.scheme, device=local, keepalive=(setup,))
+    if args.host_chunks is not None:
+        L.check(L.dll.xf_set_host_overlap(eng.ctx, args.host_chunks))
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
     with torch.cuda.stream(stream):
@@ -289,7 +292,7 @@ def main():
             mse = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
             mse = float(mse.item())
             e2e = {"value": inner * world * 3.0 * ke / (mse * 1e-3) / 1e6, "unit": "Mcell*stage/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                   "steps": ke, "ms_per_step": mse / ke, "api": "xf_step_host (pinned AoS U up, 1 step, AoS U down)"}
+                   "steps": ke, "ms_per_step": mse / ke, "api": "xf_step_host (pinned AoS U up in z-chunks overlapped with the plane-local part of stage 1, 1 step, AoS U down)" if args.host_chunks != 0 else "xf_step_host (pinned AoS U up, 1 step, AoS U down; no overlap)"}
         elif ke > 0:
             # N > 1: per rank, upload -> K_e steps through the slab stepper -> download, all inside the timed region
             L.check(L.dll.xf_download_aos(eng.ctx, eng.U, hptr))

@@ -156,6 +156,11 @@ int xf_stage_finish(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int fl
 /* ---- host-buffer convenience used for end-to-end timing: upload AoS U, run nsteps, download AoS U ---- */
 int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nsteps, double t_end,
                  double *d_U, double *d_U1, double *d_LU, int *steps_done, int *error);
+/* nsteps == 1 on a 3-D block: the upload goes up in `chunks` z-chunks on a copy stream while the plane-local part of stage 1
+ * (AoS->SoA, x / y ghost fill, primitive recovery, x and y sweeps) runs on each arrived chunk, and stage 3 runs in z-chunks
+ * (sweeps, update, SoA->AoS) with the download of each finished chunk behind it; bit-identical to the plain sequence.
+ * chunks <= 1 switches the overlap off (default 32). */
+int xf_set_host_overlap(xf_ctx *ctx, int chunks);
 void *xf_host_alloc_pinned(size_t bytes);
 void xf_host_free_pinned(void *p);
 

@@ -65,3 +65,34 @@ def test_checkpoint_and_restart(tmp_path, js, grid, E, cfl_extra):
     assert left == 0
     assert t == tc
     assert np.array_equal(eng.download(eng.U), Uc)
+
+
+@pytest.mark.parametrize("case,res,weno,pp,chunks", [("sbi", (40, 16, 40), 5, 0, 8), ("sbi", (24, 12, 27), 6, 1, 5), ("jet", (24, 12, 24), 7, 0, 3)])
+def test_host_step_overlapped_upload_is_bitwise_identical(case, res, weno, pp, chunks):
+    """xf_step_host with the chunked upload overlapped with the plane-local part of stage 1 (the bench's e2e leg) against the plain
+    upload -> step -> download sequence: identical bits in the returned host buffer, over several steps."""
+    import ctypes as C
+    import xfgpu  # noqa: F401
+    from xfluids_b200 import capi, host
+    SET = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json"}
+    cli = ["-run=%d,%d,%d" % res, "-weno=%d" % weno] + (["-pp=1", "-cfl=0.9"] if pp else [])
+    s = host.Setup(os.path.join(xfref.REPO, "settings", SET[case]), cli)
+    U0, T0 = s.initial_condition()
+    outs = []
+    for nch in (0, chunks):
+        eng = capi.Engine(s.block, s.thermal, s.scheme, device=0, keepalive=(s,))
+        L = eng.L
+        L.check(L.dll.xf_set_host_overlap(eng.ctx, nch))
+        eng.set_state(U0, T0)
+        eng.boundary(eng.U, s.bc)
+        assert eng.update_states(eng.U) == 0          # primitives + the dt maxima of the state the host buffer holds
+        h = np.ascontiguousarray(eng.download(eng.U))
+        hp = h.ctypes.data_as(C.c_void_p).value
+        for _ in range(4):
+            done, err = eng.step_host(hp, s.bc, 1)
+            assert (done, err) == (1, 0)
+        outs.append((h.copy(), eng.time()[0], eng.get_scalar("T").copy()))
+        eng.close()
+    assert outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][2], outs[1][2])

@@ -76,6 +76,7 @@ _PROTOS = {
     "xf_stage_interior": (C.c_int, [_P, _P, _P, C.c_int]),
     "xf_stage_finish": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_step_host": (C.c_int, [_P, _P, _BC, C.c_int, C.c_double, _P, _P, _P, _IP, _IP]),
+    "xf_set_host_overlap": (C.c_int, [_P, C.c_int]),
     "xf_host_alloc_pinned": (_P, [C.c_size_t]),
     "xf_host_free_pinned": (None, [_P]),
     "xf_launch_count": (C.c_longlong, [_P]),

@@ -69,6 +69,9 @@ struct xf_ctx
 	const XfTable *t = nullptr;
 	std::vector<void *> owned;      // device allocations freed in xf_destroy
 	double *stage = nullptr;        // device staging for AoS import/export [Ncells*E]
+	cudaStream_t copy_stream = nullptr;   // chunked host upload of xf_step_host
+	std::vector<cudaEvent_t> chunk_ev;
+	int host_chunks = 32;           // z-chunks of the overlapped upload (xf_set_host_overlap; <= 1: plain path)
 	double *h_pin = nullptr;        // pinned host scratch (16 doubles)
 	int *h_err = nullptr;           // pinned host error word (4 ints)
 	long long launches = 0;
@@ -223,6 +226,10 @@ extern "C"
 			cudaFree(p);
 		if (c->stage)
 			cudaFree(c->stage);
+		for (cudaEvent_t e : c->chunk_ev)
+			cudaEventDestroy(e);
+		if (c->copy_stream)
+			cudaStreamDestroy(c->copy_stream);
 		if (c->h_pin)
 			cudaFreeHost(c->h_pin);
 		if (c->h_err)
@@ -274,7 +281,7 @@ extern "C"
 		if (ensure_stage(c))
 			return XF_ERR_CUDA;
 		CU(cudaMemcpyAsync(c->stage, h_aos, c->ncells() * c->E * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-		KL(c->t->layout(c->d, c->E, d_field, c->stage, 1, c->stream));
+		KL(c->t->layout(c->d, c->E, d_field, c->stage, 1, c->stream, 0, -1));
 		c->launches++;
 		CU(cudaStreamSynchronize(c->stream));
 		return XF_OK;
@@ -283,7 +290,7 @@ extern "C"
 	{
 		if (ensure_stage(c))
 			return XF_ERR_CUDA;
-		KL(c->t->layout(c->d, c->E, const_cast<double *>(d_field), c->stage, 0, c->stream));
+		KL(c->t->layout(c->d, c->E, const_cast<double *>(d_field), c->stage, 0, c->stream, 0, -1));
 		c->launches++;
 		CU(cudaMemcpyAsync(h_aos, c->stage, c->ncells() * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
@@ -339,7 +346,7 @@ extern "C"
 	// ---- block-level entry points ---------------------------------------------------------------
 	int xf_boundary(xf_ctx *c, double *U, const int bc[6])
 	{
-		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches));
+		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches, 7, -1, -1));
 		return XF_OK;
 	}
 	// planes [k0, k1) ; reset_dt: zero the dt maxima first (the first call of a gather)
@@ -388,7 +395,7 @@ extern "C"
 	}
 	int xf_get_lu(xf_ctx *c, const double *U, double *LU)
 	{
-		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches, 7));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches, 7, -1, -1, -1, -1));
 		KL(c->t->lu(c->d, c->E, LU, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -410,7 +417,7 @@ extern "C"
 	{
 		if (flag < 1 || flag > 3)
 			return fail(XF_ERR_ARG, "flag must be 1..3");
-		KL(c->t->rk(c->d, c->E, U, U1, LU, dt, nullptr, flag, 0, 0, c->stream));
+		KL(c->t->rk(c->d, c->E, U, U1, LU, dt, nullptr, flag, 0, 0, c->stream, -1, -1));
 		c->launches++;
 		return XF_OK;
 	}
@@ -454,9 +461,9 @@ extern "C"
 		// by the last UpdateStates) -> gather the maxima there
 		if ((rc = update_states(c, UI, flag == 3)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 7));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 7, -1, -1, -1, -1));
 		// flux divergence + NaN guard + RK update in one kernel; LU stays in registers
-		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 		c->launches++;
 		return XF_OK;
 	}
@@ -469,7 +476,7 @@ extern "C"
 		int rc;
 		if ((rc = update_states_range(c, UI, flag == 3, true, c->d.Bz, c->d.Zmax - c->d.Bz)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 3));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 3, -1, -1, -1, -1));
 		return XF_OK;
 	}
 	int xf_stage_finish(xf_ctx *c, double *U, double *U1, double *LU, int flag)
@@ -482,8 +489,8 @@ extern "C"
 			return rc;
 		if ((rc = update_states_range(c, UI, flag == 3, false, c->d.Zmax - c->d.Bz, c->d.Zmax)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 4));
-		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 4, -1, -1, -1, -1));
+		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 		c->launches++;
 		return XF_OK;
 	}
@@ -612,10 +619,10 @@ extern "C"
 			for (int dir = 0; dir < 3; dir++)
 			{
 				CU(cudaEventRecord(ev[e++], c->stream));
-				KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 1 << dir));
+				KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 1 << dir, -1, -1, -1, -1));
 			}
 			CU(cudaEventRecord(ev[e++], c->stream));
-			KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream));
+			KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 			c->launches++;
 		}
 		CU(cudaEventRecord(ev[e++], c->stream));
@@ -737,13 +744,133 @@ extern "C"
 		return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
 	}
 	void xf_host_free_pinned(void *p) { cudaFreeHost(p); }
+	int xf_set_host_overlap(xf_ctx *c, int chunks)
+	{
+		c->host_chunks = chunks < 0 ? 0 : chunks;
+		return XF_OK;
+	}
+	// One step from a host buffer with the upload overlapped: the AoS image goes up in z-chunks on a copy stream while the compute
+	// stream converts each arrived chunk to the SoA layout and runs the plane-local part of stage 1 on it (x / y ghost fill,
+	// primitive recovery, x and y sweeps).  The planes within 2 Bz of the z faces wait for the z ghost fill, which must read the
+	// conserved variables BEFORE the primitive recovery renormalises the species (the same ordering rule as the z-halo split).
+	// Every cell goes through the same kernels on the same inputs as in the plain path: the result is bit-identical.
+	static int step_host_overlapped(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
+	{
+		const XfDev &d = c->d;
+		const int Bz = d.Bz, Zmax = d.Zmax;
+		int rc;
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		if (!c->copy_stream)
+			CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		const int nch = c->host_chunks;
+		if ((int)c->chunk_ev.size() < nch + 1)
+		{
+			const size_t old = c->chunk_ev.size();
+			c->chunk_ev.resize(nch + 1);
+			for (size_t i = old; i < c->chunk_ev.size(); i++)
+				CU(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+		}
+		const size_t plane_aos = (size_t)d.Xmax * d.Ymax * c->E; // doubles per z-plane of the AoS image
+		// the copy stream must not overwrite the staging buffer while an earlier call still reads it
+		CU(cudaEventRecord(c->chunk_ev[nch], c->stream));
+		CU(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nch], 0));
+		for (int ch = 0; ch < nch; ch++)
+		{
+			const int z0 = (int)((long long)Zmax * ch / nch), z1 = (int)((long long)Zmax * (ch + 1) / nch);
+			CU(cudaMemcpyAsync(c->stage + plane_aos * z0, h_U + plane_aos * z0, plane_aos * (z1 - z0) * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+			CU(cudaEventRecord(c->chunk_ev[ch], c->copy_stream));
+		}
+		if ((rc = xf_dt_device(c, t_end))) // dt from the maxima the previous step left (the device state is the host buffer's)
+			return rc;
+		const int lo = 2 * Bz, hi = Zmax - 2 * Bz; // planes [lo, hi) do not feed the z ghost fill
+		for (int ch = 0; ch < nch; ch++)
+		{
+			const int z0 = (int)((long long)Zmax * ch / nch), z1 = (int)((long long)Zmax * (ch + 1) / nch);
+			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[ch], 0));
+			KL(c->t->layout(d, c->E, U, c->stage, 1, c->stream, (long long)z0 * d.Ymax, (long long)(z1 - z0) * d.Ymax));
+			c->launches++;
+			CU(cudaMemcpy2DAsync(U1 + (size_t)z0 * d.sZ, (size_t)d.N * sizeof(double), U + (size_t)z0 * d.sZ, (size_t)d.N * sizeof(double),
+								 (size_t)(z1 - z0) * d.sZ * sizeof(double), c->E, cudaMemcpyDeviceToDevice, c->stream));
+			KL(c->t->bc(d, c->E, c->cop, U, bc, c->stream, &c->launches, 3, z0, z1));
+			const int p0 = z0 > lo ? z0 : lo, p1 = z1 < hi ? z1 : hi;
+			if (p1 > p0)
+			{
+				if ((rc = update_states_range(c, U, false, false, p0, p1)))
+					return rc;
+				KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, p0, p1, -1, -1));
+			}
+		}
+		// the z ghost fill, then the planes that waited for it
+		KL(c->t->bc(d, c->E, c->cop, U, bc, c->stream, &c->launches, 4, -1, -1));
+		if ((rc = update_states_range(c, U, false, false, 0, lo)) || (rc = update_states_range(c, U, false, false, hi, Zmax)))
+			return rc;
+		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, Bz, lo, -1, -1));
+		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, hi, Zmax - Bz, -1, -1));
+		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 4, -1, -1, -1, -1));
+		KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 1, 1, 1, c->stream, -1, -1));
+		c->launches++;
+		if ((rc = xf_rk_stage(c, U, U1, LU, bc, 2)))
+			return rc;
+		// stage 3 in z-chunks with the download behind it: ghost fill and primitive recovery of U1 on the whole block (they gather the
+		// dt maxima of the next step), then per chunk of z tiles the three sweeps, the update of the planes whose two z faces are
+		// now known, the SoA->AoS conversion of those planes and their copy to the host on the copy stream.
+		if ((rc = xf_boundary(c, U1, bc)) || (rc = update_states(c, U1, true)))
+			return rc;
+		const int TF = xf_strict::z_tile_faces(), ntz = xf_strict::xf_z_tiles(d), Zi = d.Zi;
+		const int nd = nch < ntz ? nch : ntz;
+		if ((int)c->chunk_ev.size() < nch + 1 + nd)
+		{
+			const size_t old = c->chunk_ev.size();
+			c->chunk_ev.resize(nch + 1 + nd);
+			for (size_t i = old; i < c->chunk_ev.size(); i++)
+				CU(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+		}
+		for (int ch = 0; ch < nd; ch++)
+		{
+			const int t0 = (int)((long long)ntz * ch / nd), t1 = (int)((long long)ntz * (ch + 1) / nd);
+			// tiles [t0, t1) = z faces Bz - 1 + TF t0 .. Bz - 2 + TF t1  ->  inner planes (0-based) [ka, kb) have both faces
+			int ka = TF * t0 - 1, kb = TF * t1 - 1;
+			ka = ka < 0 ? 0 : ka, kb = kb > Zi ? Zi : kb;
+			if (ch == nd - 1)
+				kb = Zi;
+			KL(c->t->sweeps(d, c->ns, c->cop, U1, c->stream, &c->launches, 3, Bz + ka, Bz + kb, -1, -1));
+			KL(c->t->sweeps(d, c->ns, c->cop, U1, c->stream, &c->launches, 4, -1, -1, t0, t1));
+			KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 3, 1, 1, c->stream, ka, kb));
+			c->launches++;
+			// planes to ship: the updated inner planes, plus the z ghost planes with the first / last chunk
+			const int z0 = ch == 0 ? 0 : Bz + ka, z1 = ch == nd - 1 ? Zmax : Bz + kb;
+			KL(c->t->layout(d, c->E, U, c->stage, 0, c->stream, (long long)z0 * d.Ymax, (long long)(z1 - z0) * d.Ymax));
+			c->launches++;
+			CU(cudaEventRecord(c->chunk_ev[nch + 1 + ch], c->stream));
+			CU(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[nch + 1 + ch], 0));
+			CU(cudaMemcpyAsync(h_U + plane_aos * z0, c->stage + plane_aos * z0, plane_aos * (z1 - z0) * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+		}
+		int f[4];
+		if ((rc = xf_error_flags(c, f))) // synchronises the compute stream
+			return rc;
+		CU(cudaStreamSynchronize(c->copy_stream));
+		const int err = (f[0] || f[1] || f[2]) ? 1 : 0;
+		if (steps_done)
+			*steps_done = 1;
+		if (error)
+			*error = err;
+		return err ? XF_ERR_NUMERIC : XF_OK;
+	}
 	int xf_step_host(xf_ctx *c, double *h_U, const int bc[6], int nsteps, double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
 	{
 		int rc;
-		if ((rc = xf_upload_aos(c, U, h_U)))
-			return rc;
-		CU(cudaMemcpyAsync(U1, U, xf_field_doubles(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-		rc = xf_run(c, U, U1, LU, bc, nsteps, t_end, steps_done, nullptr, error);
+		const XfDev &d = c->d;
+		const bool overlap = c->host_chunks > 1 && nsteps == 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks;
+		if (overlap)
+			return step_host_overlapped(c, h_U, bc, t_end, U, U1, LU, steps_done, error); // downloads as it goes
+		else
+		{
+			if ((rc = xf_upload_aos(c, U, h_U)))
+				return rc;
+			CU(cudaMemcpyAsync(U1, U, xf_field_doubles(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+			rc = xf_run(c, U, U1, LU, bc, nsteps, t_end, steps_done, nullptr, error);
+		}
 		if (rc && rc != XF_ERR_NUMERIC)
 			return rc;
 		int rc2 = xf_download_aos(c, U, h_U);

@@ -439,7 +439,7 @@ constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
 template <class C, int DIR, int WENO, bool PP>
-__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw)
+__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */)
 {
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
 	extern __shared__ double smem[];
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
 		// grid: x = XF_TX-cell chunks of the linear index space of one z-plane, y = inner plane (32-bit index arithmetic;
 		// stencils of valid faces never leave their row, so cells outside the plane only feed idle threads)
-		const int kpl = d.Bz + blockIdx.y;
+		const int kpl = kp0 + blockIdx.y;
 		const int q0 = blockIdx.x * XF_TX;
 		const long long id0 = (long long)kpl * d.sZ + q0;
 		id_l = id0 + threadIdx.x;
@@ -487,13 +487,13 @@ __global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? X
 		// planes run close together, so the 5 (7) halo planes of a z tile come from L2 instead of DRAM a second time (ncu: 43.9 GB
 		// read per launch with the z tile as the slowest block index, vs 30.2 GB in x / y)
 		const int bx = blockIdx.x;
-		sweep_tile = blockIdx.y;
+		sweep_tile = blockIdx.y + (DIR == 2 ? kp0 : 0);
 		const int i = d.Bx + bx * XF_TW + tx;
 		// faces along the sweep start at B-1 ; the other transverse index is inner
 		int j, k, f0;
 		long long sS; // cell stride along the sweep
 		if constexpr (DIR == 1)
-			f0 = d.By - 1 + sweep_tile * XF_TF, k = d.Bz + blockIdx.z, j = 0, sS = d.sY;
+			f0 = d.By - 1 + sweep_tile * XF_TF, k = kp0 + blockIdx.z, j = 0, sS = d.sY;
 		else
 			f0 = d.Bz - 1 + sweep_tile * XF_TF, j = d.By + blockIdx.z, k = 0, sS = d.sZ;
 		const int nmax = DIR == 1 ? d.Ymax : d.Zmax;
@@ -565,34 +565,35 @@ __device__ __forceinline__ bool inner_cell(const XfDev &d, long long &id)
 #ifndef XF_RK_TILE
 #define XF_RK_TILE 8 // > 0: walk the (y, z) plane of blocks in XF_RK_TILE x XF_RK_TILE tiles (z fastest inside a tile, tiles y fastest); 0: z-fastest columns.  Measured 512x512x256: 18.0 -> 15.0 ms per step (tile 4, 8, 16 alike)
 #endif
-__device__ __forceinline__ bool inner_cell_zfast(const XfDev &d, long long &id)
+// ka, nz: inner z-planes [ka, ka + nz) of the block (0 <= ka, ka + nz <= Zi)
+__device__ __forceinline__ bool inner_cell_zfast(const XfDev &d, long long &id, int ka, int nz)
 {
 	const long long b = blockIdx.x;
 	int j, k, xc;
 	if (XF_RK_TILE > 0)
 	{
 		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 1;
-		const int nty = (d.Yi + TT - 1) / TT, ntz = (d.Zi + TT - 1) / TT;
+		const int nty = (d.Yi + TT - 1) / TT, ntz = (nz + TT - 1) / TT;
 		const unsigned per_x = unsigned(nty) * unsigned(ntz) * (TT * TT);
 		xc = int(b / per_x);
 		const unsigned r = unsigned(b - (long long)xc * per_x);
 		const unsigned tile = r / (TT * TT), w = r % (TT * TT);
 		k = int(tile / nty) * TT + int(w % TT);
 		j = int(tile % nty) * TT + int(w / TT);
-		if (j >= d.Yi || k >= d.Zi)
+		if (j >= d.Yi || k >= nz)
 			return false;
 	}
 	else
 	{
-		k = int(b % d.Zi);
-		const long long r = b / d.Zi;
+		k = int(b % nz);
+		const long long r = b / nz;
 		j = int(r % d.Yi);
 		xc = int(r / d.Yi);
 	}
 	const int i = xc * blockDim.x + threadIdx.x;
 	if (i >= d.Xi)
 		return false;
-	id = ((long long)(k + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
+	id = ((long long)(k + ka + d.Bz) * d.Ymax + (j + d.By)) * d.Xp + (i + d.Bx);
 	return true;
 }
 __device__ __forceinline__ double lu_of(const XfDev &d, long long o)
@@ -627,10 +628,10 @@ __device__ __forceinline__ double rk_of(double U, double U1, double LU, double d
 // dt_dev != nullptr: read dt from the device (graph-replayable); guard: check UI (U1,U1,U for flag 1,2,3) and LU
 template <int E, bool FUSED_LU>
 __global__ void __launch_bounds__(256) k_rk(XfDev d, double *__restrict__ U, double *__restrict__ U1, const double *__restrict__ LU,
-											double dt_host, const double *__restrict__ dt_dev, int flag, int guard)
+											double dt_host, const double *__restrict__ dt_dev, int flag, int guard, int ka, int nz)
 {
 	long long id;
-	if (FUSED_LU ? !inner_cell_zfast(d, id) : !inner_cell(d, id))
+	if (FUSED_LU ? !inner_cell_zfast(d, id, ka, nz) : !inner_cell(d, id))
 		return;
 	const double dt = dt_dev ? *dt_dev : dt_host;
 	bool bad = false;
@@ -734,7 +735,7 @@ __device__ __forceinline__ void bc_apply(const XfDev &d, double *__restrict__ U,
 	}
 }
 template <int E, int DIR>
-__global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int bc_min, int bc_max, int cop)
+__global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int bc_min, int bc_max, int cop, int k0, int k1 /* z-planes [k0, k1) for DIR 0, 1 */)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int i, j, k, g;
@@ -742,8 +743,8 @@ __global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int
 	{ // threads over (j,k) x g ; g fastest is pointless for coalescing here, ghost columns are 4 wide
 		g = int(t % d.Bx);
 		const long long r = t / d.Bx;
-		j = int(r % d.Ymax), k = int(r / d.Ymax);
-		if (k >= d.Zmax)
+		j = int(r % d.Ymax), k = k0 + int(r / d.Ymax);
+		if (k >= k1)
 			return;
 		bc_apply<E, 0>(d, U, bc_min, g, j, k, 0, d.Bx, 1, cop);
 		bc_apply<E, 0>(d, U, bc_max, g + d.Xmax - d.Bx, j, k, d.Xi, d.Xmax - d.Bx - 1, -1, cop);
@@ -752,8 +753,8 @@ __global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int
 	{
 		i = int(t % d.Xmax);
 		const long long r = t / d.Xmax;
-		g = int(r % d.By), k = int(r / d.By);
-		if (k >= d.Zmax)
+		g = int(r % d.By), k = k0 + int(r / d.By);
+		if (k >= k1)
 			return;
 		bc_apply<E, 1>(d, U, bc_min, i, g, k, 0, d.By, 1, cop);
 		bc_apply<E, 1>(d, U, bc_max, i, g + d.Ymax - d.By, k, d.Yi, d.Ymax - d.By - 1, -1, cop);
@@ -775,10 +776,10 @@ __global__ void __launch_bounds__(256) k_bc(XfDev d, double *__restrict__ U, int
 // that both sides are coalesced; scalar arrays padded/unpadded; z-slab halo pack/unpack.
 // ---------------------------------------------------------------------------------------------
 template <int E, bool TO_SOA>
-__global__ void __launch_bounds__(128) k_layout(XfDev d, double *__restrict__ soa, double *__restrict__ aos)
+__global__ void __launch_bounds__(128) k_layout(XfDev d, double *__restrict__ soa, double *__restrict__ aos, long long row0)
 {
 	__shared__ double tile[128 * E];
-	const long long row = blockIdx.x;                 // k*Ymax + j  (grid.x: up to 2^31-1 rows)
+	const long long row = row0 + blockIdx.x;          // k*Ymax + j  (grid.x: up to 2^31-1 rows)
 	const int i0 = blockIdx.y * 128;
 	const int ni = min(128, d.Xmax - i0);
 	const long long abase = (row * d.Xmax + i0) * E;  // AoS doubles
@@ -883,8 +884,10 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 }
 
 template <class C, int DIR, int WENO, bool PP>
-static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s)
+static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1)
 {
+	if (kp1 <= kp0)
+		return 0;
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST;
 	static bool attr_done = false;
 	if constexpr (DIR == 0)
@@ -892,8 +895,8 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s)
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
 		if (!attr_done)
 			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
-		const dim3 g((unsigned)((d.sZ + XF_TX - 1) / XF_TX), (unsigned)d.Zi);
-		k_sweep<C, DIR, WENO, PP><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0]);
+		const dim3 g((unsigned)((d.sZ + XF_TX - 1) / XF_TX), (unsigned)(kp1 - kp0));
+		k_sweep<C, DIR, WENO, PP><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0], kp0);
 	}
 	else
 	{
@@ -902,41 +905,44 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s)
 			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
 		dim3 g;
 		if (DIR == 1)
-			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = d.Zi;
+			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = kp1 - kp0;
 		else
-			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Zi + 1 + XF_TF - 1) / XF_TF, g.z = d.Yi;
-		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR]);
+			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = kp1 - kp0, g.z = d.Yi; // kp0, kp1: tile range of the z sweep
+		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR], kp0);
+		(void)kp1;
 	}
 	XF_CHECK_LAUNCH();
 	return 0;
 }
 template <class C, int DIR, int WENO>
-static int sweep_t(const XfDev &d, const double *U, cudaStream_t s)
+static int sweep_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1)
 {
-	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s) : sweep_pp_t<C, DIR, WENO, false>(d, U, s);
+	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s, kp0, kp1) : sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1);
 }
+// kp0, kp1: z-plane range [kp0, kp1) of the x and y sweeps (absolute plane indices inside [Bz, Bz + Zi)); the z sweep always
+// covers the block
 template <class C>
-static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask)
+static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1)
 {
 	int rc = 0;
 	const bool dx = d.DimX && (dirmask & 1), dy = d.DimY && (dirmask & 2), dz = d.DimZ && (dirmask & 4);
 	if (d.weno == 7)
 	{
-		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s, kp0, kp1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s, kp0, kp1), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s, tz0, tz1), ++*launches;
 	}
 	else if (d.weno == 6)
 	{
-		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s, kp0, kp1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s, kp0, kp1), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s, tz0, tz1), ++*launches;
 	}
 	else
 	{
-		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s, kp0, kp1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s, kp0, kp1), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s, tz0, tz1), ++*launches;
 	}
 	return rc;
 }
@@ -964,10 +970,18 @@ int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, 
 {
 	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s, launches, k0, k1));
 }
-int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask)
+// kp0, kp1: z-plane range of the x / y sweeps (< 0: all inner planes); tz0, tz1: tile range of the z sweep (tile t = faces
+// Bz - 1 + XF_TF t ... ; < 0: all xf_z_tiles() of them)
+int xf_z_tiles(const XfDev &d) { return (d.Zi + 1 + XF_TF - 1) / XF_TF; }
+int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1)
 {
-	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask));
+	if (kp0 < 0)
+		kp0 = d.Bz, kp1 = d.Bz + d.Zi;
+	if (tz0 < 0)
+		tz0 = 0, tz1 = xf_z_tiles(d);
+	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1));
 }
+int z_tile_faces() { return XF_TF; }
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 int launch_lu(const XfDev &d, int E_, double *LU, cudaStream_t s)
 {
@@ -976,20 +990,27 @@ int launch_lu(const XfDev &d, int E_, double *LU, cudaStream_t s)
 	XF_CHECK_LAUNCH();
 	return 0;
 }
-int launch_rk(const XfDev &d, int E_, double *U, double *U1, const double *LU, double dt, const double *dt_dev, int flag, int guard, int fused, cudaStream_t s)
+// fused: ka, kb = inner z-planes [ka, kb) to update (ka < 0: all)
+int launch_rk(const XfDev &d, int E_, double *U, double *U1, const double *LU, double dt, const double *dt_dev, int flag, int guard, int fused, cudaStream_t s,
+			  int ka, int kb)
 {
 	const long long n = (long long)d.Xi * d.Yi * d.Zi;
+	if (ka < 0)
+		ka = 0, kb = d.Zi;
+	const int nz = kb - ka;
 	if (fused)
 	{
-		long long nb = (long long)((d.Xi + 255) / 256) * d.Yi * d.Zi; // one block per (x chunk, y, z), z fastest
+		if (nz <= 0)
+			return 0;
+		long long nb = (long long)((d.Xi + 255) / 256) * d.Yi * nz; // one block per (x chunk, y, z), z fastest
 		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 1;
 		if (XF_RK_TILE > 0)
-			nb = (long long)((d.Xi + 255) / 256) * ((d.Yi + TT - 1) / TT) * ((d.Zi + TT - 1) / TT) * (TT * TT);
-		XF_DISPATCH_E(E_, k_rk<E, true><<<(unsigned)nb, 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
+			nb = (long long)((d.Xi + 255) / 256) * ((d.Yi + TT - 1) / TT) * ((nz + TT - 1) / TT) * (TT * TT);
+		XF_DISPATCH_E(E_, k_rk<E, true><<<(unsigned)nb, 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard, ka, nz));
 	}
 	else
 	{
-		XF_DISPATCH_E(E_, k_rk<E, false><<<nblk(n, 256), 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard));
+		XF_DISPATCH_E(E_, k_rk<E, false><<<nblk(n, 256), 256, 0, s>>>(d, U, U1, LU, dt, dt_dev, flag, guard, 0, d.Zi));
 	}
 	XF_CHECK_LAUNCH();
 	return 0;
@@ -1001,26 +1022,29 @@ int launch_nan(const XfDev &d, int E_, const double *UI, const double *LU, cudaS
 	XF_CHECK_LAUNCH();
 	return 0;
 }
-int launch_bc(const XfDev &d, int E_, int cop, double *U, const int bc[6], cudaStream_t s, long long *launches)
+// dirmask: bit d = fill direction d; k0, k1: z-plane range of the x and y fills (k0 < 0: all planes)
+int launch_bc(const XfDev &d, int E_, int cop, double *U, const int bc[6], cudaStream_t s, long long *launches, int dirmask, int k0, int k1)
 {
-	if (d.DimX && !(bc[0] == 0 && bc[1] == 0))
+	if (k0 < 0)
+		k0 = 0, k1 = d.Zmax;
+	if (d.DimX && (dirmask & 1) && !(bc[0] == 0 && bc[1] == 0) && k1 > k0)
 	{
-		const long long n = (long long)d.Bx * d.Ymax * d.Zmax;
-		XF_DISPATCH_E(E_, k_bc<E, 0><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[0], bc[1], cop));
+		const long long n = (long long)d.Bx * d.Ymax * (k1 - k0);
+		XF_DISPATCH_E(E_, k_bc<E, 0><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[0], bc[1], cop, k0, k1));
 		XF_CHECK_LAUNCH();
 		++*launches;
 	}
-	if (d.DimY)
+	if (d.DimY && (dirmask & 2) && k1 > k0)
 	{
-		const long long n = (long long)d.Xmax * d.By * d.Zmax;
-		XF_DISPATCH_E(E_, k_bc<E, 1><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[2], bc[3], cop));
+		const long long n = (long long)d.Xmax * d.By * (k1 - k0);
+		XF_DISPATCH_E(E_, k_bc<E, 1><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[2], bc[3], cop, k0, k1));
 		XF_CHECK_LAUNCH();
 		++*launches;
 	}
-	if (d.DimZ)
+	if (d.DimZ && (dirmask & 4))
 	{
 		const long long n = (long long)d.Xmax * d.Ymax * d.Bz;
-		XF_DISPATCH_E(E_, k_bc<E, 2><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[4], bc[5], cop));
+		XF_DISPATCH_E(E_, k_bc<E, 2><<<nblk(n, 256), 256, 0, s>>>(d, U, bc[4], bc[5], cop, 0, 0));
 		XF_CHECK_LAUNCH();
 		++*launches;
 	}
@@ -1038,16 +1062,21 @@ int launch_dt_final(const XfDev &d, double t_end, cudaStream_t s)
 	XF_CHECK_LAUNCH();
 	return 0;
 }
-int launch_layout(const XfDev &d, int E_, double *soa, double *aos, int to_soa, cudaStream_t s)
+// rows [row0, row0 + nrows) of the block (row = k * Ymax + j); nrows < 0: all of them.  `aos` is the whole block's AoS image.
+int launch_layout(const XfDev &d, int E_, double *soa, double *aos, int to_soa, cudaStream_t s, long long row0, long long nrows)
 {
-	dim3 g((unsigned)((long long)d.Ymax * d.Zmax), (d.Xmax + 127) / 128);
+	if (nrows < 0)
+		row0 = 0, nrows = (long long)d.Ymax * d.Zmax;
+	if (nrows == 0)
+		return 0;
+	dim3 g((unsigned)nrows, (d.Xmax + 127) / 128);
 	if (to_soa)
 	{
-		XF_DISPATCH_E(E_, k_layout<E, true><<<g, 128, 0, s>>>(d, soa, aos));
+		XF_DISPATCH_E(E_, k_layout<E, true><<<g, 128, 0, s>>>(d, soa, aos, row0));
 	}
 	else
 	{
-		XF_DISPATCH_E(E_, k_layout<E, false><<<g, 128, 0, s>>>(d, soa, aos));
+		XF_DISPATCH_E(E_, k_layout<E, false><<<g, 128, 0, s>>>(d, soa, aos, row0));
 	}
 	XF_CHECK_LAUNCH();
 	return 0;

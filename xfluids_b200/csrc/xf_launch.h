@@ -7,15 +7,17 @@
 	namespace NS                                                                                                              \
 	{                                                                                                                         \
 		int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1); \
-		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask); \
+		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1); \
+		int xf_z_tiles(const XfDev &d);                                                                                       \
+		int z_tile_faces();                                                                                                   \
 		int launch_lu(const XfDev &d, int E, double *LU, cudaStream_t s);                                                     \
 		int launch_rk(const XfDev &d, int E, double *U, double *U1, const double *LU, double dt, const double *dt_dev,       \
-					  int flag, int guard, int fused, cudaStream_t s);                                                        \
+					  int flag, int guard, int fused, cudaStream_t s, int ka, int kb);                                        \
 		int launch_nan(const XfDev &d, int E, const double *UI, const double *LU, cudaStream_t s);                           \
-		int launch_bc(const XfDev &d, int E, int cop, double *U, const int bc[6], cudaStream_t s, long long *launches);      \
+		int launch_bc(const XfDev &d, int E, int cop, double *U, const int bc[6], cudaStream_t s, long long *launches, int dirmask, int k0, int k1); \
 		int launch_dt(const XfDev &d, const double *rho, cudaStream_t s);                                                     \
 		int launch_dt_final(const XfDev &d, double t_end, cudaStream_t s);                                                    \
-		int launch_layout(const XfDev &d, int E, double *soa, double *aos, int to_soa, cudaStream_t s);                      \
+		int launch_layout(const XfDev &d, int E, double *soa, double *aos, int to_soa, cudaStream_t s, long long row0, long long nrows); \
 		int launch_scalar_pad(const XfDev &d, double *padded, double *flat, int to_padded, cudaStream_t s);                  \
 		int launch_halo(const XfDev &d, int E, double *U, double *buf, int k0, int pack, cudaStream_t s);                    \
 	}
