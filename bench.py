@@ -141,6 +141,29 @@ def run_cpu_reference(wl, grid, nsteps, threads):
     return grid[0] * grid[1] * grid[2] * 3.0 * abs(n) / sec / 1e6, "port", sec, 1
 
 
+def bind_to_gpu_numa(local):
+    """N > 1: pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffer is allocated and first
+    touched, so that the e2e leg's 10 GB buffer lives on the NUMA node next to the GPU's PCIe root.  Best effort; returns a note."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "rank pinned to %d GPU-local CPUs" % len(cpus)
+        return "no GPU-local CPUs in this cgroup"
+    except Exception as e:  # noqa: BLE001
+        return "not pinned (%s)" % type(e).__name__
+
+
 def cpu_sample_grid(wl):
     return (128, 64, 64) if wl == "sbi" else (128, 64, 64)
 
@@ -205,7 +228,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- xfluids_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = None
     if world > 1:
+        numa_note = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
@@ -368,7 +393,7 @@ def main():
                            "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
                            "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
                            "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % (eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9),
-                           "ic_seconds_host": round(t_ic, 2)},
+                           "ic_seconds_host": round(t_ic, 2), "host_numa": numa_note},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
         if roof:
             line["roofline"] = roof

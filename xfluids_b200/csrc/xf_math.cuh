@@ -466,7 +466,11 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 	// its own k-ascending summation, so every partial sum is the one the reference forms.  (Measured, 512x256x256: sweeps
 	// 19.71 / 20.57 / 20.27 -> 18.22 / 19.68 / 19.20 ms with the component-0 hoist below; also carrying the entropy row along made
 	// it slower again, 19.74 / 21.00 / 20.58 -- profiles/r01_tuning.md.)  WENO7: 32 accumulators do not fit, rows stay separate.
+#ifdef XF_PAIR_WENO7
+	constexpr bool PAIR = true;
+#else
 	constexpr bool PAIR = (WENO != 7);
+#endif
 	if constexpr (PAIR)
 	{
 		const double lA0 = 0.5 * (b2 + un_c + b3), lB0 = 0.5 * (b2 - un_c + b3);
@@ -503,12 +507,18 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 				}
 			}
 		}
-		const double avA = (alpha == 1) ? fabs(un - R.c) : ((alpha == 2) ? lmax[0] : glf[0]);
-		const double avB = (alpha == 1) ? fabs(un + R.c) : ((alpha == 2) ? lmax[2] : glf[2]);
+		// WENO7: eigen_local == 0 (Eigen_value.hpp:29-32) -> LLF == ROE
+		const double avA = (alpha == 1 || (alpha == 2 && WENO == 7)) ? fabs(un - R.c) : ((alpha == 2) ? lmax[0] : glf[0]);
+		const double avB = (alpha == 1 || (alpha == 2 && WENO == 7)) ? fabs(un + R.c) : ((alpha == 2) ? lmax[2] : glf[2]);
 		if constexpr (WENO == 6)
 		{
 			f[0] = xf_split_wenocu6(avA, ufA[0], ufA[1], ufA[2], ufA[3], ufA[4], ufA[5], ffA[0], ffA[1], ffA[2], ffA[3], ffA[4], ffA[5], 1.e-8 * dl * dl);
 			f[E - 1] = xf_split_wenocu6(avB, ufB[0], ufB[1], ufB[2], ufB[3], ufB[4], ufB[5], ffB[0], ffB[1], ffB[2], ffB[3], ffB[4], ffB[5], 1.e-8 * dl * dl);
+		}
+		else if constexpr (WENO == 7)
+		{
+			f[0] = xf_split_weno7(avA, ufA[0], ufA[1], ufA[2], ufA[3], ufA[4], ufA[5], ufA[6], ufA[7], ffA[0], ffA[1], ffA[2], ffA[3], ffA[4], ffA[5], ffA[6], ffA[7]);
+			f[E - 1] = xf_split_weno7(avB, ufB[0], ufB[1], ufB[2], ufB[3], ufB[4], ufB[5], ufB[6], ufB[7], ffB[0], ffB[1], ffB[2], ffB[3], ffB[4], ffB[5], ffB[6], ffB[7]);
 		}
 		else if constexpr (WENO == 5)
 		{
