@@ -465,12 +465,8 @@ XF_DEV void xf_face_flux(const ST &st, const XfRoe<C> &R, int alpha, const doubl
 	// same stencil.  Projected together: one pass of shared-memory loads and E - 2 shared products per stencil value; each row keeps
 	// its own k-ascending summation, so every partial sum is the one the reference forms.  (Measured, 512x256x256: sweeps
 	// 19.71 / 20.57 / 20.27 -> 18.22 / 19.68 / 19.20 ms with the component-0 hoist below; also carrying the entropy row along made
-	// it slower again, 19.74 / 21.00 / 20.58 -- profiles/r01_tuning.md.)  WENO7: 32 accumulators do not fit, rows stay separate.
-#ifdef XF_PAIR_WENO7
-	constexpr bool PAIR = true;
-#else
-	constexpr bool PAIR = (WENO != 7);
-#endif
+	// it slower again, 19.74 / 21.00 / 20.58 -- profiles/r01_tuning.md.)
+	constexpr bool PAIR = true; // WENO7 (32 accumulators) still fits 128 registers without spilling: -1..2 %
 	if constexpr (PAIR)
 	{
 		const double lA0 = 0.5 * (b2 + un_c + b3), lB0 = 0.5 * (b2 - un_c + b3);
