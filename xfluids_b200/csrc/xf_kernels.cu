@@ -199,86 +199,155 @@ __device__ __forceinline__ bool cell_is_inner(const XfDev &d, long long id)
 	return i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
 }
 
+#ifndef XF_PRIM_PIPE
+#define XF_PRIM_PIPE 8 // 128-cell chunks per block, the next chunk's U and T prefetched with cp.async while the current one is computed (0: off).  Measured 512x256x256: off 10.1, 2: 8.79, 4: 8.43, 8: 8.26 ms per step
+#endif
+__device__ __forceinline__ void xf_cp_async8(double *smem_dst, const double *gmem_src)
+{
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src));
+}
+// one cell of the primitive recovery; Uc[0..E-1] = the cell's conserved variables, Tc = its Newton warm start
+template <class C>
+__device__ __forceinline__ void prim_cell(const XfDev &d, const XfThermo &th, double *__restrict__ U, long long id, int i, int j, int k,
+										  const double *Uc, double Tc, int flags, double *dtm, double *glf)
+{
+	constexpr int NS = C::NS, NC = C::NC;
+	PrimCell<C> pc;
+	pc.rho = Uc[0];
+	pc.rho1 = 1.0 / pc.rho;
+	if constexpr (C::COP)
+	{
+		double *yi = pc.yi;
+		if (d.ghost)
+		{ // GhostSpecies: renormalise and write back into U (Update_device.hpp:15-22)
+			yi[NC] = 0.0;
+			double sum_yi = 0.0;
+#pragma unroll
+			for (int ii = 0; ii < NC; ii++)
+				yi[ii] = Uc[5 + ii] * pc.rho1, sum_yi += yi[ii];
+			sum_yi = 1.0 / sum_yi;
+#pragma unroll
+			for (int ii = 0; ii < NC; ii++)
+				yi[ii] *= sum_yi, U[(5 + ii) * d.N + id] = pc.rho * yi[ii];
+		}
+		else
+		{
+			yi[NC] = 1.0;
+#pragma unroll
+			for (int ii = 0; ii < NC; ii++)
+				yi[ii] = Uc[5 + ii] * pc.rho1, yi[NC] += -yi[ii];
+		}
+#pragma unroll
+		for (int n = 0; n < NS; n++)
+			d.y[n * d.N + id] = yi[n];
+	}
+	pc.U1 = Uc[1], pc.U2 = Uc[2], pc.U3 = Uc[3], pc.U4 = Uc[4];
+	pc.u = pc.U1 * pc.rho1, pc.v = pc.U2 * pc.rho1, pc.w = pc.U3 * pc.rho1;
+	pc.q2 = pc.u * pc.u + pc.v * pc.v + pc.w * pc.w;
+	pc.tme = pc.U4 * pc.rho1 - 0.5 * pc.q2;
+	double T = 0.0, Cp = 0.0, hi[NS];
+	bool done = true;
+	if constexpr (C::COP)
+	{
+		double Wm = 0.0; // sum yi/Wi
+#pragma unroll
+		for (int n = 0; n < NS; n++)
+			Wm += pc.yi[n] * th._Wi[n];
+		pc.Wm = Wm, pc.R = Wm * th.Ru;
+		T = Tc;
+		done = xf_newton<C>(th, pc.yi, pc.tme, pc.R, T, 0, XF_NEWTON_FAST, true, hi, Cp);
+		if (!done)
+		{ // park: T after XF_NEWTON_FAST steps; k_prim_hard resumes at iteration XF_NEWTON_FAST + 1
+			d.T[id] = T;
+			const unsigned slot = atomicAdd(d.hard_count, 1u);
+			d.hard_ids[slot] = (unsigned)id;
+		}
+	}
+	if (done)
+	{
+		const bool inner = i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
+		double dt1[3] = {0.0, 0.0, 0.0}, gl1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+		prim_epilogue<C>(d, th, id, inner, pc, T, hi, Cp, flags, dt1, gl1);
+		if (flags & 1)
+		{
+#pragma unroll
+			for (int q = 0; q < 3; q++)
+				dtm[q] = fmax(dtm[q], dt1[q]);
+		}
+		if (flags & 2)
+		{
+#pragma unroll
+			for (int q = 0; q < 9; q++)
+				glf[q] = fmax(glf[q], gl1[q]);
+		}
+	}
+}
+
+// grid: x = chunks of 128 * max(XF_PRIM_PIPE, 1) cells of one z-plane's linear index space, y = plane (lin0 = the first plane);
+// 32-bit index arithmetic inside the plane (a 64-bit division per cell costs more instructions than the whole epilogue).
+// ncu (source-level sampling) had 30 % of this kernel's samples on the first use of the cell's freshly loaded U -- DRAM latency that
+// 20 resident warps per SM cannot hide -- hence the cp.async double buffer: each thread prefetches ITS OWN next cell (no barrier).
 template <class C>
 __global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0 /* first z-plane */, long long lin1)
 {
-#ifdef XF_PRIM_LINEAR
-	const long long lin = lin0 * d.sZ + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned jq = unsigned((lin / d.Xp) % d.Ymax), iq = unsigned(lin % d.Xp);
-	const int kq = int(lin / d.sZ);
-	const unsigned q = unsigned(lin - (long long)kq * d.sZ);
-	const bool active = lin < lin1 * d.sZ && int(iq) < d.Xmax;
-#else
-	// grid: x = 128-cell chunks of one z-plane, y = plane; 32-bit index arithmetic inside the plane (a 64-bit
-	// division per cell costs more instructions than the whole epilogue)
-	const unsigned q = blockIdx.x * 128u + threadIdx.x;
-	const unsigned jq = q / (unsigned)d.Xp, iq = q - jq * (unsigned)d.Xp;
+	constexpr int E = C::E, NV = E + (C::COP ? 1 : 0), CH = XF_PRIM_PIPE > 0 ? XF_PRIM_PIPE : 1;
 	const int kq = int(lin0) + int(blockIdx.y);
-	const bool active = q < (unsigned)d.sZ && int(iq) < d.Xmax;
-#endif
+	const long long pbase = (long long)kq * d.sZ;
 	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	(void)lin1;
-	if (active)
+#if XF_PRIM_PIPE > 0
+	__shared__ double buf[2][NV][128];
+	auto issue = [&](int c, int b)
 	{
-		const long long id = (long long)kq * d.sZ + q;
-		constexpr int NS = C::NS, NC = C::NC;
-		PrimCell<C> pc;
-		pc.rho = U[id];
-		pc.rho1 = 1.0 / pc.rho;
-		if constexpr (C::COP)
+		const unsigned q = (blockIdx.x * CH + c) * 128u + threadIdx.x;
+		if (q < (unsigned)d.sZ)
 		{
-			double *yi = pc.yi;
-			if (d.ghost)
-			{ // GhostSpecies: renormalise and write back into U (Update_device.hpp:15-22)
-				yi[NC] = 0.0;
-				double sum_yi = 0.0;
 #pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] = U[(5 + ii) * d.N + id] * pc.rho1, sum_yi += yi[ii];
-				sum_yi = 1.0 / sum_yi;
-#pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] *= sum_yi, U[(5 + ii) * d.N + id] = pc.rho * yi[ii];
-			}
-			else
-			{
-				yi[NC] = 1.0;
-#pragma unroll
-				for (int ii = 0; ii < NC; ii++)
-					yi[ii] = U[(5 + ii) * d.N + id] * pc.rho1, yi[NC] += -yi[ii];
-			}
-#pragma unroll
-			for (int n = 0; n < NS; n++)
-				d.y[n * d.N + id] = yi[n];
+			for (int n = 0; n < E; n++)
+				xf_cp_async8(&buf[b][n][threadIdx.x], U + n * d.N + pbase + q);
+			if constexpr (C::COP)
+				xf_cp_async8(&buf[b][E][threadIdx.x], d.T + pbase + q);
 		}
-		pc.U1 = U[1 * d.N + id], pc.U2 = U[2 * d.N + id], pc.U3 = U[3 * d.N + id], pc.U4 = U[4 * d.N + id];
-		pc.u = pc.U1 * pc.rho1, pc.v = pc.U2 * pc.rho1, pc.w = pc.U3 * pc.rho1;
-		pc.q2 = pc.u * pc.u + pc.v * pc.v + pc.w * pc.w;
-		pc.tme = pc.U4 * pc.rho1 - 0.5 * pc.q2;
-		double T = 0.0, Cp = 0.0, hi[NS];
-		bool done = true;
-		if constexpr (C::COP)
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	issue(0, 0);
+#endif
+#pragma unroll 1
+	for (int c = 0; c < CH; c++)
+	{
+		const unsigned q = (blockIdx.x * CH + c) * 128u + threadIdx.x;
+		const unsigned jq = q / (unsigned)d.Xp, iq = q - jq * (unsigned)d.Xp;
+		const bool active = q < (unsigned)d.sZ && int(iq) < d.Xmax;
+		double Uc[E], Tc = 0.0;
+#if XF_PRIM_PIPE > 0
+		if (c + 1 < CH)
 		{
-			double Wm = 0.0; // sum yi/Wi
-#pragma unroll
-			for (int n = 0; n < NS; n++)
-				Wm += pc.yi[n] * th._Wi[n];
-			pc.Wm = Wm, pc.R = Wm * th.Ru;
-			T = d.T[id];
-			done = xf_newton<C>(th, pc.yi, pc.tme, pc.R, T, 0, XF_NEWTON_FAST, true, hi, Cp);
-			if (!done)
-			{ // park: T after XF_NEWTON_FAST steps; k_prim_hard resumes at iteration XF_NEWTON_FAST + 1
-				d.T[id] = T;
-				const unsigned slot = atomicAdd(d.hard_count, 1u);
-				d.hard_ids[slot] = (unsigned)id;
-			}
+			issue(c + 1, (c + 1) & 1);
+			asm volatile("cp.async.wait_group 1;" ::: "memory");
 		}
-		if (done)
+		else
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+		if (active)
 		{
-			const int i = int(iq), j = int(jq), k = kq;
-			const bool inner = i >= d.Bx && i < d.Xmax - d.Bx && j >= d.By && j < d.Ymax - d.By && k >= d.Bz && k < d.Zmax - d.Bz;
-			prim_epilogue<C>(d, th, id, inner, pc, T, hi, Cp, flags, dtm, glf);
+#pragma unroll
+			for (int n = 0; n < E; n++)
+				Uc[n] = buf[c & 1][n][threadIdx.x];
+			if constexpr (C::COP)
+				Tc = buf[c & 1][E][threadIdx.x];
 		}
+#else
+		if (active)
+		{
+#pragma unroll
+			for (int n = 0; n < E; n++)
+				Uc[n] = U[n * d.N + pbase + q];
+			if constexpr (C::COP)
+				Tc = d.T[pbase + q];
+		}
+#endif
+		if (active)
+			prim_cell<C>(d, th, U, pbase + q, int(iq), int(jq), kq, Uc, Tc, flags, dtm, glf);
 	}
 	prim_reduce(d, flags, dtm, glf);
 }
@@ -853,11 +922,8 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 	// z-planes [k0, k1) of the block (all of it: 0, Zmax)
 	if (k1 <= k0)
 		return 0;
-#ifdef XF_PRIM_LINEAR
-	const dim3 nb((unsigned)((d.sZ * (k1 - k0) + 127) / 128), 1);
-#else
-	const dim3 nb((unsigned)((d.sZ + 127) / 128), (unsigned)(k1 - k0));
-#endif
+	constexpr int CHB = 128 * (XF_PRIM_PIPE > 0 ? XF_PRIM_PIPE : 1);
+	const dim3 nb((unsigned)((d.sZ + CHB - 1) / CHB), (unsigned)(k1 - k0));
 	if constexpr (C::COP)
 	{
 		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
