@@ -503,14 +503,26 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 #ifndef XF_SIDE_EARLY
 #define XF_SIDE_EARLY 0 // 1: issue the face-side loads before the stencil staging (their latency overlaps the staging)
 #endif
-constexpr int XF_TX = XF_TX_; // x-sweep: faces (cells) per block
+// x-sweep: faces (cells) per block: 128 (4 blocks/SM), except WENO-CU6, whose long instruction stream (with the limiter even more so) runs
+// better in 256-thread blocks, 2 per SM, like the y / z sweeps: with four 128-thread blocks at four different places of the code
+// "no instruction" was its top stall reason (ncu, CU6 + limiter: 2.24 stalled warps per issue in x, absent in y / z).  Measured
+// (512x256x256, x sweep ms per step, 128 vs 256): WENO5+PP 20.5 / 21.0, CU6 33.9 / 33.3, CU6+PP 41.6 / 36.0, WENO7 36.3 / 37.2, WENO7+PP 38.8 / 39.4
+#ifndef XF_TX_BIG
+#define XF_TX_BIG 256
+#endif
+template <int WENO, bool PP>
+struct XfTx
+{
+	static constexpr int V = (WENO != 6) ? XF_TX_ : XF_TX_BIG;
+	static constexpr int MINB = (WENO != 6) ? XF_MINB_X : (512 / XF_TX_BIG);
+};
 constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
 template <class C, int DIR, int WENO, bool PP>
-__global__ void __launch_bounds__(DIR == 0 ? XF_TX : XF_TW * XF_TF, DIR == 0 ? XF_MINB_X : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */)
+__global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, DIR == 0 ? XfTx<WENO, PP>::MINB : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */)
 {
-	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P;
+	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P, XF_TX = XfTx<WENO, PP>::V;
 	extern __shared__ double smem[];
 	XfSide<C> sl, sr;
 	XfRoe<C> R;
@@ -958,6 +970,7 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, 
 	static bool attr_done = false;
 	if constexpr (DIR == 0)
 	{
+		constexpr int XF_TX = XfTx<WENO, PP>::V;
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
 		if (!attr_done)
 			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
