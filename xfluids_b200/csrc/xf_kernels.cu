@@ -516,7 +516,10 @@ struct XfTx
 	static constexpr int V = (WENO != 6) ? XF_TX_ : XF_TX_BIG;
 	static constexpr int MINB = (WENO != 6) ? XF_MINB_X : (512 / XF_TX_BIG);
 };
-constexpr int XF_TW = 32;     // y/z sweeps: tile width in x
+#ifndef XF_TW_
+#define XF_TW_ 32
+#endif
+constexpr int XF_TW = XF_TW_; // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
 template <class C, int DIR, int WENO, bool PP>
