@@ -134,7 +134,7 @@ class Engine:
     def __init__(self, block, thermal, scheme, device=0, keepalive=()):
         self.L = Lib.get()
         self._keep = (block, thermal, scheme) + tuple(keepalive)
-        self.block = block
+        self.block, self.scheme = block, scheme
         self.ctx = _P()
         self.L.check(self.L.dll.xf_create(C.byref(block), C.byref(thermal), C.byref(scheme), device, C.byref(self.ctx)))
         self.E = self.L.dll.xf_emax(self.ctx)

@@ -861,7 +861,10 @@ extern "C"
 	{
 		int rc;
 		const XfDev &d = c->d;
-		const bool overlap = c->host_chunks > 1 && nsteps == 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks;
+		// GLF needs the block-wide maxima of |lambda| of THIS stage's primitives before any sweep starts (ConVenction_block.hpp:115-215):
+		// no chunk-wise overlap of primitive recovery and sweeps there
+		const bool overlap = c->host_chunks > 1 && nsteps == 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks &&
+							 c->sc.artificial_type != 3;
 		if (overlap)
 			return step_host_overlapped(c, h_U, bc, t_end, U, U1, LU, steps_done, error); // downloads as it goes
 		else

@@ -67,6 +67,10 @@ class SlabStepper:
 
     def __init__(self, eng, bc, rank, world, device, overlap=True):
         self.eng, self.bc, self.rank, self.world = eng, list(bc), rank, world
+        if world > 1 and getattr(eng, "scheme", None) is not None and eng.scheme.artificial_type == 3 and eng.scheme.weno_order != 7:
+            # GLF needs the running maxima of |lambda| over the WHOLE domain before every sweep (ConVenction_block.hpp:115-215):
+            # a per-stage MAX all-reduce between primitive recovery and sweeps, which this stepper does not do
+            raise NotImplementedError("global Lax-Friedrichs splitting (Artificial_type 3) is single-GPU only; use LLF or ROE on N > 1 GPUs")
         self.overlap = overlap and world > 1 and eng.block.DimZ
         self.comm = None
         self.hx = HaloExchanger(rank, world, self.bc)
