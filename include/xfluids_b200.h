@@ -133,6 +133,7 @@ int xf_clear_errors(xf_ctx *ctx);
  * the 3 directional dt maxima (double[3]) and the error word (int[4]). */
 double *xf_device_dtmax(xf_ctx *ctx);
 int *xf_device_errors(xf_ctx *ctx);
+double *xf_device_glfmax(xf_ctx *ctx);   /* 9 device doubles: the GLF running maxima of |lambda| (dir*3 + {u-c, u, u+c}), eigen_block_{x,y,z} of ConVenction_block.hpp:115-215 */
 
 /* ---- z-slab halo (replaces FluidMpiCopyKernelZ pack/unpack, src/solver_BCs/BCs_kernels.hpp:304-324 and
  *      MpiTrans::MpiTransBuf, src/mpiPacks/mpiPacks.cpp:357-505): Bwidth_Z planes x Emax, contiguous per component */
@@ -151,6 +152,10 @@ int xf_halo_unpack_on(xf_ctx *ctx, double *d_UI, int face, const double *d_buf, 
  *   xf_stage_finish:   primitive recovery of the z ghost planes, the z sweep, flux divergence + NaN guard + RK update
  * Results are bit-identical to xf_rk_stage. */
 int xf_stage_interior(xf_ctx *ctx, double *d_U, double *d_U1, int flag);
+/* the same stage split between primitive recovery and sweeps instead: with global Lax-Friedrichs splitting on N > 1 GPUs the caller
+ * MAX-reduces xf_device_glfmax over the ranks between the two calls (the reference's MPI build reduces eigen_block the same way) */
+int xf_stage_states(xf_ctx *ctx, double *d_U, double *d_U1, int flag);
+int xf_stage_fluxes(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
 int xf_stage_finish(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
 
 /* ---- host-buffer convenience used for end-to-end timing: upload AoS U, run nsteps, download AoS U ---- */

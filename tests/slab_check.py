@@ -52,9 +52,10 @@ def main():
     ap.add_argument("--strong", action="store_true")
     ap.add_argument("--weno", type=int, default=5)
     ap.add_argument("--pp", type=int, default=0, help="positivity-preserving limiter on, at CFL 0.9 (where it acts)")
+    ap.add_argument("--alpha", default="LLF", help="LLF | ROE | GLF (GLF: 9 running maxima MAX-reduced over the ranks every stage)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    one, mine = setups(a.case, rank, world, a.strong, ["-weno=%d" % a.weno] + (["-pp=1", "-cfl=0.9"] if a.pp else []))
+    one, mine = setups(a.case, rank, world, a.strong, ["-weno=%d" % a.weno, "-alpha=" + a.alpha] + (["-pp=1", "-cfl=0.9"] if a.pp else []))
     E, Bz = mine.Emax, mine.block.Bwidth_Z
     zi = mine.block.Z_inner
     plane = mine.block.Xmax * mine.block.Ymax * E

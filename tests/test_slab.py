@@ -37,9 +37,10 @@ def test_exchange_protocol_gloo(world, case, strong):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,strong,weno,pp", [("sbi", False, 5, 0), ("jet", True, 5, 0), ("sbi", False, 6, 1), ("sbi", False, 7, 0)])
-def test_two_slabs_equal_one_block_bitwise(case, strong, weno, pp):
+@pytest.mark.parametrize("case,strong,weno,pp,alpha", [("sbi", False, 5, 0, "LLF"), ("jet", True, 5, 0, "LLF"), ("sbi", False, 6, 1, "LLF"), ("sbi", False, 7, 0, "ROE"),
+                                                       ("sbi", False, 5, 0, "GLF"), ("jet", True, 6, 0, "GLF")])
+def test_two_slabs_equal_one_block_bitwise(case, strong, weno, pp, alpha):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5", "--weno", str(weno), "--pp", str(pp)] + (["--strong"] if strong else []))
+    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5", "--weno", str(weno), "--pp", str(pp), "--alpha", alpha] + (["--strong"] if strong else []))

@@ -68,6 +68,9 @@ _PROTOS = {
     "xf_clear_errors": (C.c_int, [_P]),
     "xf_device_dtmax": (_P, [_P]),
     "xf_device_errors": (_P, [_P]),
+    "xf_device_glfmax": (_P, [_P]),
+    "xf_stage_states": (C.c_int, [_P, _P, _P, C.c_int]),
+    "xf_stage_fluxes": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_halo_doubles": (C.c_size_t, [_P]),
     "xf_halo_pack": (C.c_int, [_P, _P, C.c_int, _P]),
     "xf_halo_unpack": (C.c_int, [_P, _P, C.c_int, _P]),

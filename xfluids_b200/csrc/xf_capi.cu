@@ -256,6 +256,7 @@ extern "C"
 	long long xf_launch_count(const xf_ctx *c) { return c->launches; }
 	double *xf_device_dtmax(xf_ctx *c) { return c->d.red + XF_RED_DTMAX; }
 	int *xf_device_errors(xf_ctx *c) { return c->d.err; }
+	double *xf_device_glfmax(xf_ctx *c) { return c->d.red + XF_RED_GLF; }
 
 	int xf_field_alloc(xf_ctx *c, double **p)
 	{
@@ -490,6 +491,23 @@ extern "C"
 		if ((rc = update_states_range(c, UI, flag == 3, false, c->d.Zmax - c->d.Bz, c->d.Zmax)))
 			return rc;
 		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 4, -1, -1, -1, -1));
+		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
+		c->launches++;
+		return XF_OK;
+	}
+	// ---- one stage split between primitive recovery and sweeps (multi-GPU GLF: the 9 running maxima of |lambda| are MAX-reduced over
+	//      the ranks in between, like the reference's MPI build does for eigen_block) ----------------------------------------------
+	int xf_stage_states(xf_ctx *c, double *U, double *U1, int flag)
+	{
+		if (flag < 1 || flag > 3)
+			return fail(XF_ERR_ARG, "flag must be 1..3");
+		return update_states(c, flag == 1 ? U : U1, flag == 3);
+	}
+	int xf_stage_fluxes(xf_ctx *c, double *U, double *U1, double *LU, int flag)
+	{
+		if (flag < 1 || flag > 3)
+			return fail(XF_ERR_ARG, "flag must be 1..3");
+		KL(c->t->sweeps(c->d, c->ns, c->cop, flag == 1 ? U : U1, c->stream, &c->launches, 7, -1, -1, -1, -1));
 		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 		c->launches++;
 		return XF_OK;

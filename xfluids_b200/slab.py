@@ -67,11 +67,11 @@ class SlabStepper:
 
     def __init__(self, eng, bc, rank, world, device, overlap=True):
         self.eng, self.bc, self.rank, self.world = eng, list(bc), rank, world
-        if world > 1 and getattr(eng, "scheme", None) is not None and eng.scheme.artificial_type == 3 and eng.scheme.weno_order != 7:
-            # GLF needs the running maxima of |lambda| over the WHOLE domain before every sweep (ConVenction_block.hpp:115-215):
-            # a per-stage MAX all-reduce between primitive recovery and sweeps, which this stepper does not do
-            raise NotImplementedError("global Lax-Friedrichs splitting (Artificial_type 3) is single-GPU only; use LLF or ROE on N > 1 GPUs")
-        self.overlap = overlap and world > 1 and eng.block.DimZ
+        # GLF needs the running maxima of |lambda| over the WHOLE domain before every sweep (ConVenction_block.hpp:115-215): a MAX
+        # all-reduce of 9 doubles between primitive recovery and sweeps of every stage; that stage runs un-overlapped
+        sc = getattr(eng, "scheme", None)
+        self.glf = world > 1 and sc is not None and sc.artificial_type == 3 and sc.weno_order != 7
+        self.overlap = overlap and world > 1 and eng.block.DimZ and not self.glf
         self.comm = None
         self.hx = HaloExchanger(rank, world, self.bc)
         L = eng.L.dll
@@ -79,6 +79,7 @@ class SlabStepper:
         self.buf = {k: torch.empty(n, dtype=torch.float64, device=device) for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
         self.dtmax = wrap_device(L.xf_device_dtmax(eng.ctx), 3, torch.float64, device)
         self.errors = wrap_device(L.xf_device_errors(eng.ctx), 4, torch.int32, device)
+        self.glfmax = wrap_device(L.xf_device_glfmax(eng.ctx), 9, torch.float64, device) if self.glf else None
 
     def halo(self, field):
         """z exchange of `field` (a device pointer of the engine): pack -> send/recv -> unpack, on the current stream."""
@@ -100,6 +101,8 @@ class SlabStepper:
         e.boundary(e.U, self.bc)
         self.halo(e.U)
         assert e.update_states(e.U) == 0
+        if self.glf:
+            self.hx.allreduce_max(self.glfmax)
 
     # ---- one stage, exchange blocking (reference order: BC + exchange, UpdateStates, GetLU, UpdateU) ----
     def stage_blocking(self, flag):
@@ -107,7 +110,13 @@ class SlabStepper:
         UI = e.U if flag == 1 else e.U1
         e.boundary(UI, self.bc)
         self.halo(UI)
-        e.rk_stage(None, flag)
+        if self.glf:
+            L = e.L
+            L.check(L.dll.xf_stage_states(e.ctx, e.U, e.U1, flag))
+            self.hx.allreduce_max(self.glfmax)
+            L.check(L.dll.xf_stage_fluxes(e.ctx, e.U, e.U1, e.LU, flag))
+        else:
+            e.rk_stage(None, flag)
 
     # ---- one stage, exchange overlapped with the interior work ----
     def stage_overlapped(self, flag):
