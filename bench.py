@@ -165,7 +165,9 @@ def bind_to_gpu_numa(local):
 
 
 def cpu_sample_grid(wl):
-    return (128, 64, 64) if wl == "sbi" else (128, 64, 64)
+    # ~12 s of work for the 16 host threads of a pool box at 5 steps (x3 stages): large enough that the OpenMP loops are not dominated by
+    # fork/join, small enough for the few-minutes budget; the reference cannot allocate 512^3 (int cellbytes, 157 GB)
+    return (256, 128, 128)
 
 
 def reference_arm(args):
