@@ -35,6 +35,11 @@ WORKLOADS = {
                 desc="shock-bubble.json Inert-SBI 3-D multi-species shock-bubble, WENO5-JS + LLF, inviscid, reactions off"),
     "jet": dict(json="expanded-jet.json", grid=(1024, 512, 512), ref="jet_w5_fast", refcase="jet", E=7, NS=3, cop=1,
                 desc="expanded-jet.json 3-D under-expanded multi-component jet, WENO5-JS + LLF, inviscid"),
+    # the 2-D single-component BASELINE configs (parity-test cases; measured with --no-cpu, no z decomposition)
+    "riemann": dict(json="2d-riemann.json", grid=(4096, 4096, 0), ref="riemann_w5_fast", refcase="riemann", E=5, NS=1, cop=0,
+                    desc="2d-riemann.json 2-D four-quadrant Riemann problem, single component, WENO5-JS + LLF"),
+    "vortex": dict(json="2d-euler-vortex.json", grid=(1024, 1024, 0), ref="vortex_w5_fast", refcase="vortex", E=5, NS=1, cop=0,
+                   desc="2d-euler-vortex.json 2-D isentropic Euler vortex, single component, WENO5-JS + LLF"),
 }
 
 
