@@ -368,6 +368,7 @@ def main():
         # capture was taken on this workload and grid
         traffic, traffic_src, executed = None, None, None
         tpath = os.path.join(REPO, "profiles", "traffic.json")
+        tj, key = {}, ""
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = "%s:%dx%dx%d:weno%d" % (args.workload, setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner, args.weno)
@@ -384,6 +385,18 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650", "copy_gbs_live": copy},
                 "ms_per_launch": t_launch * 1e3, "flops_per_face": sweep_flops_per_face(E, setup.num_species, setup.cop, args.weno),
                 "step_breakdown_ms": prof}
+        # the two HBM-side kernels against the measured copy peak: algorithmic bytes per launch / live launch time, and the
+        # DRAM bytes ncu saw for the same launch
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ncells_all = setup.ncells
+        alg = {"lu_rk": (3 * E + 2 * E + E) * 8 * inner,                                   # 3 flux fields + U, U1 + the written field
+               "prim": ((E + (1 if setup.cop else 0)) + (11 + setup.num_species + max(setup.num_species - 1, 0) if setup.cop else 6) + (max(setup.num_species - 1, 0) if setup.cop and setup.ghost_species else 0)) * 8 * ncells_all}
+        other = {}
+        for kname in ("prim", "lu_rk"):
+            tl = prof[kname] / 3.0 * 1e-3
+            other[kname] = {"bound": "hbm", "ms_per_launch": tl * 1e3, "achieved_gbs": alg[kname] / tl / 1e9, "peak_gbs": hbm_peak,
+                            "frac": alg[kname] / tl / 1e9 / hbm_peak, "traffic": (tj.get(key, {}).get(kname) if os.path.exists(tpath) else None)}
+        roof["other_kernels"] = other
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
