@@ -330,17 +330,21 @@ def main():
             L.check(L.dll.xf_download_aos(eng.ctx, eng.U, hptr))
             barrier()
             e0.record(stream)
+            overlapped = True
             for _ in range(ke):
-                eng.upload(eng.U, hU)
-                stepper.step()
-                L.check(L.dll.xf_download_aos(eng.ctx, eng.U, hptr))
+                if not stepper.step_host(hptr):      # chunked upload / download overlapped with stages 1 and 3, halo exchanges in between
+                    overlapped = False
+                    eng.upload(eng.U, hU)
+                    stepper.step()
+                    L.check(L.dll.xf_download_aos(eng.ctx, eng.U, hptr))
             e1.record(stream)
             barrier()
             mse = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
             dist.all_reduce(mse, op=dist.ReduceOp.MAX)
             mse = float(mse.item())
             e2e = {"value": inner * world * 3.0 * ke / (mse * 1e-3) / 1e6, "unit": "Mcell*stage/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
-                   "steps": ke, "ms_per_step": mse / ke, "api": "xf_upload_aos + slab step (halo over NCCL) + xf_download_aos per rank"}
+                   "steps": ke, "ms_per_step": mse / ke, "api": ("xf_host_begin / xf_host_stage1_finish / xf_host_stage3 per rank (PCIe copies in z-chunks under stages 1 and 3), halo over NCCL" if overlapped
+                           else "xf_upload_aos + slab step (halo over NCCL) + xf_download_aos per rank")}
 
         # ---- per-kernel device times of eager steps (CUDA events on the launching stream) ----
         prof = None

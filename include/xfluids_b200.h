@@ -166,6 +166,17 @@ int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nstep
  * (sweeps, update, SoA->AoS) with the download of each finished chunk behind it; bit-identical to the plain sequence.
  * chunks <= 1 switches the overlap off (default 32). */
 int xf_set_host_overlap(xf_ctx *ctx, int chunks);
+/* the same overlapped step in three pieces, for a z-slab caller that has halo exchanges to put in between (xfluids_b200/slab.py):
+ *   [MAX-reduce xf_device_dtmax over the ranks]
+ *   xf_host_begin          chunked upload + plane-local part of stage 1 on the planes that do not feed the z ghost fill / halo
+ *   [z-halo exchange of U]
+ *   xf_host_stage1_finish  z ghost fill (physical faces), the waiting planes, z sweep, update
+ *   [stage 2: xf_boundary + halo + xf_rk_stage / the split stage; then xf_boundary + halo on U1]
+ *   xf_host_stage3         primitive recovery of U1, then sweeps / update / SoA->AoS / download per z-chunk; returns when the host buffer is complete
+ * Not available (XF_ERR_ARG) for 1-D / 2-D blocks, chunks <= 1 or global Lax-Friedrichs splitting. */
+int xf_host_begin(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], double t_end, double *d_U, double *d_U1);
+int xf_host_stage1_finish(xf_ctx *ctx, const int bc[6], double *d_U, double *d_U1, double *d_LU);
+int xf_host_stage3(xf_ctx *ctx, double *h_U_aos_pinned, double *d_U, double *d_U1, double *d_LU, int *error);
 void *xf_host_alloc_pinned(size_t bytes);
 void xf_host_free_pinned(void *p);
 

@@ -122,6 +122,33 @@ def main():
             results[overlap] = (eng.download(eng.U).reshape(mine.block.Zmax, plane), eng.time()[0])
         eng.close()
     assert np.array_equal(results[False][0], results[True][0]), "overlapped exchange changed the result"
+    # host-buffer step (bench e2e on N > 1): the chunked, overlapped form against upload -> step -> download, 2 steps each
+    if a.alpha != "GLF":
+        hres = {}
+        for mode in ("plain", "overlapped"):
+            eng = capi.Engine(mine.block, mine.thermal, mine.scheme, device=local, keepalive=(mine,))
+            eng.set_stream(stream.cuda_stream)
+            eng.L.check(eng.L.dll.xf_set_host_overlap(eng.ctx, 4))
+            with torch.cuda.stream(stream):
+                eng.set_state(Um, Tm)
+                st = SlabStepper(eng, mine.bc, rank, world, dev, overlap=True)
+                st.startup()
+                st.steps(1)
+                hb = np.ascontiguousarray(eng.download(eng.U))
+                for _ in range(2):
+                    if mode == "plain":
+                        eng.upload(eng.U, hb)
+                        eng.upload(eng.U1, hb)
+                        st.step()
+                        hb = np.ascontiguousarray(eng.download(eng.U))
+                    else:
+                        assert st.step_host(hb.ctypes.data), "overlapped host step not available"
+                assert not st.any_error()
+                torch.cuda.synchronize()
+                hres[mode] = (hb.copy(), eng.time()[0])
+            eng.close()
+        assert hres["plain"][1] == hres["overlapped"][1], "host-step time differs"
+        assert np.array_equal(hres["plain"][0], hres["overlapped"][0]), "overlapped host step differs from upload/step/download"
     mineU, tmine = results[True]
     gathered = [None] * world
     dist.all_gather_object(gathered, (mineU[Bz:Bz + zi], tmine))

@@ -80,6 +80,9 @@ _PROTOS = {
     "xf_stage_finish": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_step_host": (C.c_int, [_P, _P, _BC, C.c_int, C.c_double, _P, _P, _P, _IP, _IP]),
     "xf_set_host_overlap": (C.c_int, [_P, C.c_int]),
+    "xf_host_begin": (C.c_int, [_P, _P, _BC, C.c_double, _P, _P]),
+    "xf_host_stage1_finish": (C.c_int, [_P, _BC, _P, _P, _P]),
+    "xf_host_stage3": (C.c_int, [_P, _P, _P, _P, _P, _IP]),
     "xf_host_alloc_pinned": (_P, [C.c_size_t]),
     "xf_host_free_pinned": (None, [_P]),
     "xf_launch_count": (C.c_longlong, [_P]),

@@ -772,8 +772,21 @@ extern "C"
 	// primitive recovery, x and y sweeps).  The planes within 2 Bz of the z faces wait for the z ghost fill, which must read the
 	// conserved variables BEFORE the primitive recovery renormalises the species (the same ordering rule as the z-halo split).
 	// Every cell goes through the same kernels on the same inputs as in the plain path: the result is bit-identical.
-	static int step_host_overlapped(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
+	// ---- the overlapped host step in three pieces, so that a multi-GPU caller can put its z-halo exchanges between them -------------
+	//   xf_host_begin          chunked upload + the plane-local part of stage 1 on the planes that do not feed the z ghost fill / halo
+	//   [z-halo exchange of U by the caller: the planes it packs, Bz..2Bz-1 and their mirror, are still un-renormalised]
+	//   xf_host_stage1_finish  z ghost fill, the waiting planes, z sweep, update
+	//   [stage 2 by the caller; then ghost fill + z-halo exchange of U1]
+	//   xf_host_stage3         primitive recovery of U1 (gathers the next dt), then sweeps / update / SoA->AoS / download per z-chunk
+	static bool host_overlap_ok(xf_ctx *c)
 	{
+		const XfDev &d = c->d;
+		return c->host_chunks > 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks && c->sc.artificial_type != 3;
+	}
+	int xf_host_begin(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1)
+	{
+		if (!host_overlap_ok(c))
+			return fail(XF_ERR_ARG, "xf_host_begin: needs a 3-D block, host_chunks > 1 and ROE / LLF splitting");
 		const XfDev &d = c->d;
 		const int Bz = d.Bz, Zmax = d.Zmax;
 		int rc;
@@ -819,6 +832,13 @@ extern "C"
 				KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, p0, p1, -1, -1));
 			}
 		}
+		return XF_OK;
+	}
+	int xf_host_stage1_finish(xf_ctx *c, const int bc[6], double *U, double *U1, double *LU)
+	{
+		const XfDev &d = c->d;
+		const int Bz = d.Bz, Zmax = d.Zmax, lo = 2 * Bz, hi = Zmax - 2 * Bz;
+		int rc;
 		// the z ghost fill, then the planes that waited for it
 		KL(c->t->bc(d, c->E, c->cop, U, bc, c->stream, &c->launches, 4, -1, -1));
 		if ((rc = update_states_range(c, U, false, false, 0, lo)) || (rc = update_states_range(c, U, false, false, hi, Zmax)))
@@ -828,12 +848,20 @@ extern "C"
 		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 4, -1, -1, -1, -1));
 		KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 1, 1, 1, c->stream, -1, -1));
 		c->launches++;
-		if ((rc = xf_rk_stage(c, U, U1, LU, bc, 2)))
-			return rc;
-		// stage 3 in z-chunks with the download behind it: ghost fill and primitive recovery of U1 on the whole block (they gather the
+		return XF_OK;
+	}
+	int xf_host_stage3(xf_ctx *c, double *h_U, double *U, double *U1, double *LU, int *error)
+	{
+		const XfDev &d = c->d;
+		const int Bz = d.Bz, Zmax = d.Zmax, nch = c->host_chunks;
+		const size_t plane_aos = (size_t)d.Xmax * d.Ymax * c->E;
+		int rc;
+		if (!host_overlap_ok(c) || !c->copy_stream)
+			return fail(XF_ERR_ARG, "xf_host_stage3 without xf_host_begin");
+		// stage 3 in z-chunks with the download behind it: primitive recovery of U1 on the whole block (its ghost fill / halo was the caller's; gathers the
 		// dt maxima of the next step), then per chunk of z tiles the three sweeps, the update of the planes whose two z faces are
 		// now known, the SoA->AoS conversion of those planes and their copy to the host on the copy stream.
-		if ((rc = xf_boundary(c, U1, bc)) || (rc = update_states(c, U1, true)))
+		if ((rc = update_states(c, U1, true)))
 			return rc;
 		const int TF = xf_strict::z_tile_faces(), ntz = xf_strict::xf_z_tiles(d), Zi = d.Zi;
 		const int nd = nch < ntz ? nch : ntz;
@@ -869,11 +897,19 @@ extern "C"
 			return rc;
 		CU(cudaStreamSynchronize(c->copy_stream));
 		const int err = (f[0] || f[1] || f[2]) ? 1 : 0;
-		if (steps_done)
-			*steps_done = 1;
 		if (error)
 			*error = err;
 		return err ? XF_ERR_NUMERIC : XF_OK;
+	}
+	static int step_host_overlapped(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
+	{
+		int rc;
+		if ((rc = xf_host_begin(c, h_U, bc, t_end, U, U1)) || (rc = xf_host_stage1_finish(c, bc, U, U1, LU)) || (rc = xf_rk_stage(c, U, U1, LU, bc, 2)) ||
+			(rc = xf_boundary(c, U1, bc)))
+			return rc;
+		if (steps_done)
+			*steps_done = 1;
+		return xf_host_stage3(c, h_U, U, U1, LU, error);
 	}
 	int xf_step_host(xf_ctx *c, double *h_U, const int bc[6], int nsteps, double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
 	{
@@ -881,8 +917,7 @@ extern "C"
 		const XfDev &d = c->d;
 		// GLF needs the block-wide maxima of |lambda| of THIS stage's primitives before any sweep starts (ConVenction_block.hpp:115-215):
 		// no chunk-wise overlap of primitive recovery and sweeps there
-		const bool overlap = c->host_chunks > 1 && nsteps == 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks &&
-							 c->sc.artificial_type != 3;
+		const bool overlap = nsteps == 1 && host_overlap_ok(c);
 		if (overlap)
 			return step_host_overlapped(c, h_U, bc, t_end, U, U1, LU, steps_done, error); // downloads as it goes
 		else

@@ -12,6 +12,8 @@ computes that list).  Per RK stage, after the local ghost fill in x and y:
 and once per step the three directional dt maxima are MAX-reduced over the ranks (Fluids.cpp:902-913; max is exact, so every
 rank derives the same dt bit for bit).  This module holds the transport-independent part; the device kernels are
 xf_halo_pack / xf_halo_unpack of the C ABI."""
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -159,6 +161,31 @@ class SlabStepper:
                 self.stage_overlapped(flag)
             else:
                 self.stage_blocking(flag)
+
+    def step_host(self, h_ptr, t_end=1e300):
+        """One step from / to this rank's pinned host buffer (AoS U of its slab) with the PCIe copies overlapped like xf_step_host:
+        chunked upload under the plane-local part of stage 1, stage 3 in z-chunks with the download behind it; the z-halo
+        exchanges sit between the pieces.  Bit-identical to upload -> step() -> download.  Returns False when the overlapped path
+        does not apply (GLF, 1-D / 2-D) and the caller has to use the plain sequence."""
+        e, L = self.eng, self.eng.L
+        if self.glf or not e.block.DimZ:
+            return False
+        bc = (C.c_int * 6)(*self.bc)
+        self.hx.allreduce_max(self.dtmax)
+        rc = L.dll.xf_host_begin(e.ctx, C.c_void_p(h_ptr), bc, t_end, e.U, e.U1)
+        if rc != 0:
+            return False
+        self.halo(e.U)
+        L.check(L.dll.xf_host_stage1_finish(e.ctx, bc, e.U, e.U1, e.LU))
+        if self.overlap:
+            self.stage_overlapped(2)
+        else:
+            self.stage_blocking(2)
+        e.boundary(e.U1, self.bc)
+        self.halo(e.U1)
+        err = C.c_int()
+        L.check(L.dll.xf_host_stage3(e.ctx, C.c_void_p(h_ptr), e.U, e.U1, e.LU, C.byref(err)), allow_numeric=True)
+        return True
 
     def steps(self, n, t_end=1e300):
         for _ in range(n):
