@@ -111,3 +111,19 @@ def test_no_cpu_fallback_without_gpu():
     s = setup_for("vortex", (16, 16, 0))
     with pytest.raises(capi.XfError):
         capi.Engine(s.block, s.thermal, s.scheme)
+
+
+def test_scheme_switches_from_cli_and_json(tmp_path):
+    """-weno=6 (WENO-CU6), -pp= / equations.PositivityPreserving, -cfl= and -alpha= reach the xf_scheme / xf_block the engine is created with."""
+    s = setup_for("sbi", (16, 8, 8), weno=6, extra=["-pp=1", "-cfl=0.9", "-alpha=GLF"])
+    assert (s.scheme.weno_order, s.scheme.positivity, s.scheme.artificial_type, s.scheme.fp_mode) == (6, 1, 3, 0)
+    assert s.block.CFLnumber == 0.9
+    s = setup_for("sbi", (16, 8, 8))
+    assert (s.scheme.weno_order, s.scheme.positivity, s.scheme.artificial_type) == (5, 0, 2) and s.block.CFLnumber == 0.4
+    # the JSON key (read_json.cpp:68) without any command-line override
+    src = open(os.path.join(REPO, "settings", "shock-bubble.json")).read()
+    assert '"PositivityPreserving": false' in src
+    p = tmp_path / "sbi_pp.json"
+    p.write_text(src.replace('"PositivityPreserving": false', '"PositivityPreserving": true'))
+    s = host.Setup(str(p), ["-run=16,8,8"])
+    assert s.scheme.positivity == 1
