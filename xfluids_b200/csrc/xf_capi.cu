@@ -914,9 +914,8 @@ extern "C"
 	int xf_step_host(xf_ctx *c, double *h_U, const int bc[6], int nsteps, double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
 	{
 		int rc;
-		const XfDev &d = c->d;
-		// GLF needs the block-wide maxima of |lambda| of THIS stage's primitives before any sweep starts (ConVenction_block.hpp:115-215):
-		// no chunk-wise overlap of primitive recovery and sweeps there
+		// (host_overlap_ok: not for GLF, which needs the block-wide maxima of |lambda| of THIS stage's primitives before any sweep starts,
+		// ConVenction_block.hpp:115-215 -- no chunk-wise overlap of primitive recovery and sweeps there)
 		const bool overlap = nsteps == 1 && host_overlap_ok(c);
 		if (overlap)
 			return step_host_overlapped(c, h_U, bc, t_end, U, U1, LU, steps_done, error); // downloads as it goes
