@@ -188,6 +188,12 @@ int xf_profile_step(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const 
 /* roofline denominators measured on `device`: FP64 FMA rate (TFLOP/s, FMA = 2 flop), copy bandwidth (GB/s, read+write) */
 int xf_measure_peaks(int device, double *dfma_tflops, double *copy_gbs);
 
+/* y[i] = the device logarithm of x[i] (host arrays, evaluated on `device`).  The NASA-9 enthalpy's log(T) (reference
+ * src/solver_Ini/Thermo_device.h:62-80) is the one non-IEEE-basic operation of the path; the device version replays glibc's
+ * table-driven algorithm so that it matches the reference CPU path bit for bit (csrc/xf_log.cuh); this entry point lets the
+ * tests prove it against the host libm. */
+int xf_log_eval(int device, const double *h_x, double *h_y, size_t n);
+
 /* kernel launch counter (bench.py "gpu_launches") */
 long long xf_launch_count(const xf_ctx *ctx);
 

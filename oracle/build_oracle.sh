@@ -4,7 +4,7 @@
 set -euo pipefail
 HERE=$(cd "$(dirname "$0")" && pwd)
 mkdir -p "$HERE/_build"
-g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared "$HERE/xf_oracle.cpp" -o "$HERE/_build/liboracle.so"
+g++ -std=c++17 -O2 -ffp-contract=off -fopenmp -fPIC -shared "$HERE/xf_oracle.cpp" -o "$HERE/_build/liboracle.so"
 # throughput flavour for bench.py's cpu_baseline "port" leg (contraction allowed, like the reference's fast build)
 g++ -std=c++17 -O3 -march=x86-64-v3 -fopenmp -fPIC -shared "$HERE/xf_oracle.cpp" -o "$HERE/_build/liboracle_fast.so"
 # conditioning experiment: the same restatement with log() perturbed by 1 ulp on half of its arguments

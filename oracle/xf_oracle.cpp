@@ -1083,6 +1083,15 @@ static double GetDt(const xo_cfg &c, xo_state &s)
 extern "C"
 {
 	size_t xo_ncells(const xo_cfg *c) { return size_t(c->Xmax) * c->Ymax * c->Zmax; }
+	// y[i] = this machine's libm log(x[i]) -- the reference CPU path's logarithm (get_Enthalpy_NASA, Thermo_device.h:62-80), against which
+	// tests/test_xf_log.py checks the device logarithm bit for bit.  Called through a volatile pointer: no builtin expansion.
+	void xo_libm_log(const double *x, double *y, size_t n)
+	{
+		double (*volatile f)(double) = std::log;
+#pragma omp parallel for
+		for (long long i = 0; i < (long long)n; i++)
+			y[i] = f(x[i]);
+	}
 
 	xo_state *xo_state_create(const xo_cfg *c)
 	{

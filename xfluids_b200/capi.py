@@ -88,6 +88,7 @@ _PROTOS = {
     "xf_launch_count": (C.c_longlong, [_P]),
     "xf_profile_step": (C.c_int, [_P, _P, _P, _P, _BC, C.c_double, C.c_float * 8]),
     "xf_measure_peaks": (C.c_int, [C.c_int, _DP, _DP]),
+    "xf_log_eval": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
 }
 
 EXPORTED_SYMBOLS = sorted(_PROTOS)
@@ -130,6 +131,15 @@ def measure_peaks(device=0):
     a, b = C.c_double(), C.c_double()
     L.check(L.dll.xf_measure_peaks(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def log_eval(x, device=0):
+    """The device logarithm (csrc/xf_log.cuh) of a host array, evaluated on `device`."""
+    L = Lib.get()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    L.check(L.dll.xf_log_eval(device, _dptr(x), _dptr(y), x.size))
+    return y
 
 
 class Engine:

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/xfluids_b200.h"
 #include "xf_launch.h"
+#include "xf_log.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &m)
@@ -114,9 +115,38 @@ __global__ void __launch_bounds__(256) k_peak_copy(const double2 *__restrict__ i
 		out[i] = in[i];
 }
 
+__global__ void __launch_bounds__(256) k_log_eval(const double *__restrict__ x, double *__restrict__ y, size_t n)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		y[i] = xf_log(x[i]);
+}
+
 extern "C"
 {
 	const char *xf_last_error(void) { return g_err.c_str(); }
+
+	// y[i] = xf_log(x[i]) evaluated on `device` (host arrays): the parity test of the device logarithm against the host libm
+	int xf_log_eval(int device, const double *h_x, double *h_y, size_t n)
+	{
+		CU(cudaSetDevice(device));
+		double *dx = nullptr, *dy = nullptr;
+		CU(cudaMalloc((void **)&dx, n * sizeof(double)));
+		if (cudaMalloc((void **)&dy, n * sizeof(double)) != cudaSuccess)
+		{
+			cudaFree(dx);
+			return fail(XF_ERR_CUDA, "xf_log_eval: cudaMalloc");
+		}
+		cudaError_t e = cudaMemcpy(dx, h_x, n * sizeof(double), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess)
+		{
+			k_log_eval<<<1184, 256>>>(dx, dy, n);
+			e = cudaMemcpy(h_y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
+		}
+		cudaFree(dx), cudaFree(dy);
+		if (e != cudaSuccess)
+			return fail(XF_ERR_CUDA, std::string("xf_log_eval: ") + cudaGetErrorString(e));
+		return XF_OK;
+	}
 
 	int xf_create(const xf_block *bl, const xf_thermal *th, const xf_scheme *sc, int device, xf_ctx **out)
 	{

@@ -12,6 +12,7 @@
 // {Utils_device.hpp,Eigen_matrix.hpp,Eigen_callback.h}, include/global_marco.h.
 #pragma once
 #include "xf_types.h"
+#include "xf_log.cuh"
 
 #define XF_DEV __device__ __forceinline__
 #if !defined(XF_THERMO_STATIC) && !defined(XF_THERMO_DYN)
@@ -106,7 +107,7 @@ XF_DEV double xf_mix_cp(const XfThermo &th, const double *yi, double T0)
 template <class C>
 XF_DEV void xf_species_h(const XfThermo &th, double T0, double *hi)
 {
-	const double T = xf_max(T0, 200.0), lnT = log(T), _T = 1.0 / T;
+	const double T = xf_max(T0, 200.0), lnT = xf_log(T), _T = 1.0 / T; // glibc's log, bit for bit (xf_log.cuh)
 	const int r = xf_range(T);
 #ifdef XF_THERMO_DYN
 #pragma unroll
