@@ -10,6 +10,10 @@ shock-bubble interaction (Inert-SBI, Emax = 9), WENO5-JS + LLF, 512^3 inner cell
 a ghost-plane halo exchange per stage (NCCL send/recv) and a MAX all-reduce of the dt maxima per step.
 
 value      = inner cells of all ranks * 3 * K / (device time of the K steps, max over ranks) / 1e6, state resident in HBM
+N > 1      : the C++ slab stepper (csrc/xf_slab.cu: NCCL send/recv of the ghost planes overlapped with interior work, MAX all-reduce
+             of dt) drives every rank; before anything is timed a small bitwise check of the decomposed run against the undecomposed
+             block runs through the same stepper ("slab_check": "bitwise"), and after the weak-scaling measurement the jet
+             (BASELINE configs[4], 1024x512x512 cut in z) is timed on the same ranks and on rank 0 alone ("strong": {...})
 e2e        = the same through xf_step_host: every step uploads the AoS state from pinned host memory, runs the step, and
              downloads the AoS state (what the reference's per-step CopyToUbak does, src/XFLUIDS.cpp:174,644)
 roofline   = the dominant kernel (the slowest directional sweep) against the FP64 FMA rate measured on this device
@@ -198,6 +202,114 @@ def reference_arm(args):
     return 0
 
 
+def slab_check(rank, world, local, dev, steps=3):
+    """N > 1, before anything is timed: a small shock-bubble block (32 x 16 x 16 per rank, weak) advanced `steps` steps by the C++
+    slab stepper on all ranks must equal, BIT FOR BIT, the undecomposed block advanced on rank 0's GPU alone (strict mode: no
+    floating-point reduction crosses ranks except max).  Returns "bitwise" on every rank or raises."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from xfluids_b200 import capi, host
+    from xfluids_b200.slab import SlabStepper
+    js, grid, dom = os.path.join(REPO, "settings", "shock-bubble.json"), (32, 16, 16), (0.1, 0.05, 0.05)
+    cli = ["-weno=5", "-alpha=LLF", "-pp=0"]
+    mine = host.Setup(js, ["-run=%d,%d,%d" % grid, "-mpi=1,1,%d" % world, "-mpi-s=weak"] + cli, rank=rank, nranks=world)
+    Um, Tm = mine.initial_condition()
+    eng = capi.Engine(mine.block, mine.thermal, mine.scheme, device=local, keepalive=(mine,))
+    st = SlabStepper(eng, mine.bc, rank, world, dev)
+    eng.set_state(Um, Tm)
+    st.startup()
+    done, t, err = st.run(steps)
+    assert (done, err) == (steps, 0), (done, err)
+    Bz, zi, E = mine.block.Bwidth_Z, mine.block.Z_inner, mine.Emax
+    plane = mine.block.Xmax * mine.block.Ymax * E
+    slab = eng.download(eng.U).reshape(mine.block.Zmax, plane)[Bz:Bz + zi]
+    st.close()
+    eng.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (slab, t))
+    ok = [1]
+    if rank == 0:
+        one = host.Setup(js, ["-run=%d,%d,%d" % (grid[0], grid[1], grid[2] * world), "-domain=%.17g,%.17g,%.17g" % (dom[0], dom[1], dom[2] * world)] + cli)
+        U1, T1 = one.initial_condition()
+        e1 = capi.Engine(one.block, one.thermal, one.scheme, device=local, keepalive=(one,))
+        e1.set_state(U1, T1)
+        e1.boundary(e1.U, one.bc)
+        assert e1.update_states(e1.U) == 0
+        d1, t1, err1 = e1.run(one.bc, steps)
+        Uone = e1.download(e1.U).reshape(one.block.Zmax, plane)
+        e1.close()
+        ok = [int((d1, err1) == (steps, 0) and all(g[1] == t1 and np.array_equal(g[0], Uone[Bz + r * zi:Bz + (r + 1) * zi]) for r, g in enumerate(gathered)))]
+    dist.broadcast_object_list(ok, src=0)
+    if not ok[0]:
+        raise SystemExit("bench.py: slab_check FAILED -- the decomposed run differs from the undecomposed block")
+    return "bitwise"
+
+
+def time_steps(run_steps, barrier, stream, dev, world, nwarm, nsteps):
+    """W warm-up steps, then K steps between CUDA events on the launching stream, barrier + synchronize on both sides; ms = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    run_steps(nwarm)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(nsteps)
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def strong_leg(args, rank, world, local, dev, stream, barrier):
+    """BASELINE configs[4]: the under-expanded jet, 1024 x 512 x 512, cut into `world` z-slabs (strong scaling), and the same box on
+    rank 0's GPU alone for the efficiency denominator.  Returns the sub-record (rank 0) or None."""
+    import numpy as np
+    import torch
+    from xfluids_b200 import capi, host
+    from xfluids_b200.slab import SlabStepper
+    w = WORKLOADS["jet"]
+    grid = w["grid"]
+    cli = ["-run=%d,%d,%d" % grid, "-weno=5", "-alpha=LLF", "-fp=%d" % args.fp, "-pp=0"]
+    js = os.path.join(REPO, "settings", w["json"])
+    cells = grid[0] * grid[1] * grid[2]
+    nst, nwarm = max(3, min(args.steps, 5)), 3
+    out = {}
+    for leg in ("slabs", "one"):
+        if leg == "one" and rank != 0:
+            barrier()
+            continue
+        setup = host.Setup(js, cli + (["-mpi=1,1,%d" % world, "-mpi-s=strong"] if leg == "slabs" else []), rank=rank if leg == "slabs" else 0, nranks=world if leg == "slabs" else 1)
+        U, T = setup.initial_condition()
+        eng = capi.Engine(setup.block, setup.thermal, setup.scheme, device=local, keepalive=(setup,))
+        eng.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            eng.set_state(U, T)
+            del U, T
+            if leg == "slabs":
+                st = SlabStepper(eng, setup.bc, rank, world, dev)
+                st.startup()
+                ms = time_steps(st.steps, barrier, stream, dev, world, nwarm, nst)
+                assert not st.any_error(), "numerical guard fired in the strong-scaling leg"
+                st.close()
+            else:
+                eng.boundary(eng.U, setup.bc)
+                assert eng.update_states(eng.U) == 0
+                ms = time_steps(lambda n: eng.run(setup.bc, n), lambda: torch.cuda.synchronize(), stream, dev, 1, nwarm, nst)
+                assert eng.error_flags()[:3] == [0, 0, 0]
+        eng.close()
+        out[leg] = cells * 3.0 * nst / (ms * 1e-3) / 1e6
+        if leg == "one":
+            barrier()
+    if rank != 0:
+        return None
+    return {"workload": w["desc"] + "; %dx%dx%d inner cells cut into %d z-slabs" % (grid[0], grid[1], grid[2], world), "scaling": "strong", "n_gpus": world, "steps": nst,
+            "value": out["slabs"], "unit": "Mcell*stage/s", "n1_value": out["one"], "efficiency_vs_n1": out["slabs"] / (world * out["one"]),
+            "note": "n1_value: the same box on rank 0's GPU alone, same run (xf_run graph replay)"}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -214,7 +326,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-steps", type=int, default=2)
-    ap.add_argument("--host-chunks", type=int, default=None, help="z-chunks of the overlapped upload in the e2e leg (xf_set_host_overlap; 0 = plain sequence; default: the library's 8)")
+    ap.add_argument("--host-chunks", type=int, default=None, help="z-chunks of the overlapped upload in the e2e leg (xf_set_host_overlap; 0 = plain sequence; default: the library's 32)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling jet sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -252,6 +365,7 @@ def main():
     ncells = setup.ncells
     inner = setup.block.X_inner * setup.block.Y_inner * setup.block.Z_inner
     L = capi.Lib.get()
+    check = slab_check(rank, world, local, dev) if world > 1 else None
 
     # ---- initial condition written straight into pinned host memory (the e2e leg's host buffer) ----
     nbytes = ncells * E * 8
@@ -264,6 +378,7 @@ def main():
     t_ic = time.time() - t0
 
     eng = capi.Engine(setup.block, setup.thermal, setup.scheme, device=local, keepalive=(setup,))
+    ws_gb = eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9
     if args.host_chunks is not None:
         L.check(L.dll.xf_set_host_overlap(eng.ctx, args.host_chunks))
     stream = torch.cuda.Stream(device=dev)
@@ -295,16 +410,9 @@ def main():
             sampler.start()
         l0 = eng.launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run_steps(args.steps)
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = time_steps(run_steps, barrier, stream, dev, world, 0, args.steps)
         clocks = sampler.stop() if rank == 0 else None
         launches = eng.launches() - l0
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
         assert not stepper.any_error(), "numerical guard fired during the timed region"
         value = inner * world * 3.0 * args.steps / (ms * 1e-3) / 1e6
 
@@ -332,7 +440,9 @@ def main():
             e0.record(stream)
             overlapped = True
             for _ in range(ke):
-                if not stepper.step_host(hptr):      # chunked upload / download overlapped with stages 1 and 3, halo exchanges in between
+                applied, herr = stepper.step_host(hptr)      # chunked upload / download overlapped with stages 1 and 3, halo exchanges in between
+                assert herr == 0, "numerical guard fired in the e2e leg"
+                if not applied:
                     overlapped = False
                     eng.upload(eng.U, hU)
                     stepper.step()
@@ -346,6 +456,22 @@ def main():
                    "steps": ke, "ms_per_step": mse / ke, "api": ("xf_host_begin / xf_host_stage1_finish / xf_host_stage3 per rank (PCIe copies in z-chunks under stages 1 and 3), halo over NCCL" if overlapped
                            else "xf_upload_aos + slab step (halo over NCCL) + xf_download_aos per rank")}
 
+        if e2e is not None:
+            # what bounds e2e: this rank's PCIe link, measured with the same pinned buffer and nothing else running (h2d first: the
+            # d2h pass then restores nothing we need -- the buffer is not used again), next to the rates the e2e step achieved
+            a_, b_ = C.c_double(), C.c_double()
+            barrier()
+            L.check(L.dll.xf_measure_pcie(eng.ctx, C.c_void_p(hptr), nbytes, C.byref(a_), C.byref(b_)))
+            link = torch.tensor([a_.value, b_.value], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(link, op=dist.ReduceOp.MIN)
+            sec = e2e["ms_per_step"] * 1e-3
+            e2e.update(h2d_gbs_per_rank=nbytes / sec / 1e9, d2h_gbs_per_rank=nbytes / sec / 1e9,
+                       link_h2d_gbs=float(link[0].item()), link_d2h_gbs=float(link[1].item()),
+                       copy_floor_ms=(nbytes / float(link[0].item()) + nbytes / float(link[1].item())) / 1e6,
+                       limiter="PCIe: the two copies alone take copy_floor_ms of the step's ms_per_step (link rates: slowest rank, all ranks copying at once only in the e2e leg itself); "
+                               "ghost cells travel too (the reference's Ubak layout), %.1f %% of the bytes" % (100.0 * (1.0 - inner / float(ncells))))
+
         # ---- per-kernel device times of eager steps (CUDA events on the launching stream) ----
         prof = None
         if rank == 0 and world == 1 and args.profile_steps > 0:
@@ -355,6 +481,14 @@ def main():
                 for k, v in p.items():
                     acc[k] = acc.get(k, 0.0) + v / args.profile_steps
             prof = acc
+    strong = None
+    if world > 1 and not args.no_strong and args.workload == "sbi" and args.grid is None:
+        # free the weak-scaling state first: the jet box on rank 0 alone needs most of the HBM
+        stepper.close()
+        eng.close()
+        L.dll.xf_host_free_pinned(hptr)
+        hptr = None
+        strong = strong_leg(args, rank, world, local, dev, stream, barrier)
     roof = None
     if prof:
         dfma, copy = capi.measure_peaks(local)
@@ -379,8 +513,19 @@ def main():
             if key in tj and top in tj[key]:
                 traffic, traffic_src = tj[key][top], tj.get("source")
                 executed = tj[key].get("executed")
-        roof = {"bound": "fp64", "kernel": "k_sweep<%s>" % top[-1], "achieved": fl / t_launch / 1e12, "peak": dfma, "unit": "TFLOP/s",
-                "frac": fl / t_launch / 1e12 / dfma if dfma else None, "traffic": traffic, "traffic_source": traffic_src,
+        # the honest utilisation figure first: FP64 instructions the kernel EXECUTES per face (ncu, committed capture) / launch time, against
+        # the FP64 issue rate of this device (one warp instruction per 2 cycles per SM sub-partition = half the DFMA probe's flop rate)
+        inst_face = sum(executed["fp64_thread_inst_per_face"].values()) if executed and "fp64_thread_inst_per_face" in executed else None
+        issue_peak = dfma / 2.0 if dfma else None                                          # T thread-instructions / s
+        frac_issue = (inst_face * faces / t_launch / 1e12 / issue_peak) if (inst_face and issue_peak) else None
+        roof = {"bound": "fp64", "kernel": "k_sweep<%s>" % top[-1],
+                "frac_issue": frac_issue, "fp64_inst_per_face_executed": inst_face, "issue_peak_tinst_per_s": issue_peak,
+                "achieved": fl / t_launch / 1e12, "peak": dfma, "unit": "TFLOP/s",
+                "frac": fl / t_launch / 1e12 / dfma if dfma else None, "frac_vs_nominal_37": fl / t_launch / 1e12 / 37.0,
+                "peaks_used": "frac_issue and frac: the DFMA rate measured live on this device (xf_measure_peaks; profiles/r02_peaks.json has the committed probe "
+                              "with clocks); frac_vs_nominal_37: BASELINE.md's nominal 37 TFLOP/s.  `achieved` counts the reference's dense arithmetic (SURVEY 8d "
+                              "flop model), frac_issue the instructions actually executed",
+                "traffic": traffic, "traffic_source": traffic_src,
                 # `achieved` counts the reference's dense E x E arithmetic (SURVEY 8d flop model); what the kernel EXECUTES (structural
                 # zeros skipped, strict mode = no FMA contraction) and how busy the FP64 pipe is, from the committed ncu capture:
                 "executed_ncu": executed,
@@ -398,6 +543,8 @@ def main():
         other = {}
         for kname in ("prim", "lu_rk"):
             tl = prof[kname] / 3.0 * 1e-3
+            if tl <= 0.0:      # the marching sweeps carry the divergence and the update: no separate kernel
+                continue
             other[kname] = {"bound": "hbm", "ms_per_launch": tl * 1e3, "achieved_gbs": alg[kname] / tl / 1e9, "peak_gbs": hbm_peak,
                             "frac": alg[kname] / tl / 1e9 / hbm_peak, "traffic": (tj.get(key, {}).get(kname) if os.path.exists(tpath) else None)}
         roof["other_kernels"] = other
@@ -416,16 +563,22 @@ def main():
                 "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "positivity_preserving": bool(args.pp), "flux_splitting": "LLF",
                            "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
                            "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
-                           "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % (eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9),
+                           "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % ws_gb,
                            "ic_seconds_host": round(t_ic, 2), "host_numa": numa_note},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+        if check:
+            line["slab_check"] = check
+        if strong:
+            line["strong"] = strong
         if roof:
             line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    L.dll.xf_host_free_pinned(hptr)
-    eng.close()
+    if hptr:
+        L.dll.xf_host_free_pinned(hptr)
+        stepper.close()
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -147,16 +147,46 @@ int xf_halo_unpack_on(xf_ctx *ctx, double *d_UI, int face, const double *d_buf, 
  * barrier-fenced, BCs_block.cpp:50-217 / mpiPacks.cpp:405-494):
  *   xf_boundary -> xf_halo_pack -> [send/recv + xf_halo_unpack_on a second stream]
  *   xf_stage_interior: primitive recovery of the planes that do not depend on the incoming halo (all but the z ghosts) and
- *                      the x and y sweeps (they only read inner z planes)
+ *                      the x and y sweeps (they only read inner z planes), each adding its part of the flux divergence to d_LU
  *   [wait for the unpack]
- *   xf_stage_finish:   primitive recovery of the z ghost planes, the z sweep, flux divergence + NaN guard + RK update
+ *   xf_stage_finish:   primitive recovery of the z ghost planes, the z sweep with its part of the divergence, NaN guard + RK update
  * Results are bit-identical to xf_rk_stage. */
-int xf_stage_interior(xf_ctx *ctx, double *d_U, double *d_U1, int flag);
+int xf_stage_interior(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
 /* the same stage split between primitive recovery and sweeps instead: with global Lax-Friedrichs splitting on N > 1 GPUs the caller
  * MAX-reduces xf_device_glfmax over the ranks between the two calls (the reference's MPI build reduces eigen_block the same way) */
 int xf_stage_states(xf_ctx *ctx, double *d_U, double *d_U1, int flag);
 int xf_stage_fluxes(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
 int xf_stage_finish(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, int flag);
+
+/* ---- multi-GPU: z-slab decomposition over the GPUs of one box (csrc/xf_slab.cu) -------------------------------------------------
+ * Replaces the reference's MPI layer for this path: MpiTrans::MpiTransBuf / FluidMpiCopyKernelZ (src/mpiPacks/mpiPacks.cpp:357-505,
+ * src/solver_BCs/BCs_block.cpp:50-217) and the MPI_Allreduce(MAX) of Fluid::GetFluidDt (src/Fluids.cpp:902-913).  Transport: NCCL
+ * send/recv over NVLink + all-reduce(MAX), loaded at run time (libnccl.so.2).  One xf_comm per rank; ranks are processes
+ * (torchrun) or threads of one process (`xfluids -mpi=1,1,N`).  Rank r owns Z_inner planes; its z faces carry XF_BC_COPY towards
+ * a neighbour rank (the host Setup computes that list, mpiPacks.cpp:44-72; periodic z: also the two outer faces). */
+typedef struct xf_comm xf_comm;
+typedef struct xf_slab xf_slab;
+const char *xf_slab_last_error(void);
+int xf_comm_unique_id(char id[128]);                                     /* rank 0: ncclGetUniqueId; hand the bytes to every rank */
+int xf_comm_create(const char id[128], int rank, int world, int device, xf_comm **out);   /* collective over the ranks */
+int xf_comm_destroy(xf_comm *comm);
+int xf_comm_rank(const xf_comm *comm);
+int xf_comm_world(const xf_comm *comm);
+int xf_comm_allreduce_max(xf_comm *comm, double *d_values, int n, void *cuda_stream);      /* in place, device memory */
+int xf_comm_allreduce_max_int(xf_comm *comm, int *d_values, int n, void *cuda_stream);
+/* the slab stepper of one rank: bc = this rank's six face conditions; all launches go to compute_stream (xf_set_stream is called) */
+int xf_slab_create(xf_ctx *ctx, xf_comm *comm, const int bc[6], int artificial_type, int weno_order, void *compute_stream, xf_slab **out);
+int xf_slab_destroy(xf_slab *slab);
+int xf_slab_set_overlap(xf_slab *slab, int on);                          /* 0: blocking exchange (the reference's order); default on */
+int xf_slab_neighbours(const xf_slab *slab, int lo_hi[2]);               /* neighbour ranks across zmin / zmax, -1 = physical boundary */
+int xf_slab_halo(xf_slab *slab, double *d_field);                        /* pack -> send/recv -> unpack on the compute stream */
+int xf_slab_startup(xf_slab *slab, double *d_U, int *error);             /* main.cpp:44-48: ghost fill + exchange + UpdateStates */
+int xf_slab_stage(xf_slab *slab, double *d_U, double *d_U1, double *d_LU, int flag);   /* one RK stage, exchange overlapped with interior work */
+int xf_slab_step(xf_slab *slab, double *d_U, double *d_U1, double *d_LU, double t_end);   /* dt MAX-reduction + device dt + 3 stages; asynchronous */
+int xf_slab_run(xf_slab *slab, double *d_U, double *d_U1, double *d_LU, int nsteps, double t_end, int *steps_done, double *time_out, int *error);
+int xf_slab_any_error(xf_slab *slab, int *error);                        /* guard flags MAX-reduced over the ranks; synchronises */
+int xf_slab_step_host(xf_slab *slab, double *h_U_aos_pinned, double t_end, double *d_U, double *d_U1, double *d_LU, int *error);
+int xf_slab_allreduce_max_host(xf_slab *slab, double *h_values, int n);  /* n <= 8 host doubles (block-level GetFluidDt) */
 
 /* ---- host-buffer convenience used for end-to-end timing: upload AoS U, run nsteps, download AoS U ---- */
 int xf_step_host(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], int nsteps, double t_end,
@@ -174,7 +204,7 @@ int xf_set_host_overlap(xf_ctx *ctx, int chunks);
  *   [stage 2: xf_boundary + halo + xf_rk_stage / the split stage; then xf_boundary + halo on U1]
  *   xf_host_stage3         primitive recovery of U1, then sweeps / update / SoA->AoS / download per z-chunk; returns when the host buffer is complete
  * Not available (XF_ERR_ARG) for 1-D / 2-D blocks, chunks <= 1 or global Lax-Friedrichs splitting. */
-int xf_host_begin(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], double t_end, double *d_U, double *d_U1);
+int xf_host_begin(xf_ctx *ctx, double *h_U_aos_pinned, const int bc[6], double t_end, double *d_U, double *d_U1, double *d_LU);
 int xf_host_stage1_finish(xf_ctx *ctx, const int bc[6], double *d_U, double *d_U1, double *d_LU);
 int xf_host_stage3(xf_ctx *ctx, double *h_U_aos_pinned, double *d_U, double *d_U1, double *d_LU, int *error);
 void *xf_host_alloc_pinned(size_t bytes);
@@ -187,6 +217,10 @@ void xf_host_free_pinned(void *p);
 int xf_profile_step(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const int bc[6], double t_end, float ms[8]);
 /* roofline denominators measured on `device`: FP64 FMA rate (TFLOP/s, FMA = 2 flop), copy bandwidth (GB/s, read+write) */
 int xf_measure_peaks(int device, double *dfma_tflops, double *copy_gbs);
+
+/* copy rates of this context's link for `bytes` of pinned host memory (GB/s each way, nothing else running): the e2e leg's denominators.
+ * NOTE: the d2h pass overwrites the host buffer with the staging buffer's content -- call it on a scratch / about-to-be-refilled buffer. */
+int xf_measure_pcie(xf_ctx *ctx, void *h_pinned, size_t bytes, double *h2d_gbs, double *d2h_gbs);
 
 /* y[i] = the device logarithm of x[i] (host arrays, evaluated on `device`).  The NASA-9 enthalpy's log(T) (reference
  * src/solver_Ini/Thermo_device.h:62-80) is the one non-IEEE-basic operation of the path; the device version replays glibc's

@@ -53,9 +53,15 @@ def main():
     ap.add_argument("--weno", type=int, default=5)
     ap.add_argument("--pp", type=int, default=0, help="positivity-preserving limiter on, at CFL 0.9 (where it acts)")
     ap.add_argument("--alpha", default="LLF", help="LLF | ROE | GLF (GLF: 9 running maxima MAX-reduced over the ranks every stage)")
+    ap.add_argument("--periodic-z", action="store_true", help="periodic z boundary: the outer faces of the first / last rank exchange with each other (on 2 ranks both neighbours are the same peer)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    one, mine = setups(a.case, rank, world, a.strong, ["-weno=%d" % a.weno, "-alpha=" + a.alpha] + (["-pp=1", "-cfl=0.9"] if a.pp else []))
+    extra = ["-weno=%d" % a.weno, "-alpha=" + a.alpha] + (["-pp=1", "-cfl=0.9"] if a.pp else [])
+    if a.periodic_z:
+        js, _, _ = CASES[a.case]
+        bc0 = host.Setup(os.path.join(REPO, "settings", js), []).bc
+        extra.append("-bc=" + ",".join(str(b) for b in bc0[:4] + [3, 3]))
+    one, mine = setups(a.case, rank, world, a.strong, extra)
     E, Bz = mine.Emax, mine.block.Bwidth_Z
     zi = mine.block.Z_inner
     plane = mine.block.Xmax * mine.block.Ymax * E
@@ -85,7 +91,14 @@ def main():
         if hx.hi is not None:
             work[-Bz:] = recv_hi.numpy()
         lo, hi = rank * zi, (rank + 1) * zi + 2 * Bz
-        ref = U1p[lo:hi]
+        ref = U1p[lo:hi].copy()
+        if a.periodic_z:   # the ghosts of the outer faces are the inner planes at the other end of the undecomposed block
+            ztot = zi * world
+            if rank == 0:
+                ref[:Bz] = U1p[ztot:ztot + Bz]
+            if rank == world - 1:
+                ref[-Bz:] = U1p[Bz:2 * Bz]
+            assert hx.lo == (rank - 1) % world and hx.hi == (rank + 1) % world
         if hx.lo is not None:
             assert np.array_equal(work[:Bz], ref[:Bz]), "zmin ghosts"
         if hx.hi is not None:
@@ -94,7 +107,7 @@ def main():
         m = torch.tensor([float(rank + 1), 10.0 - rank, 3.0], dtype=torch.float64)
         hx.allreduce_max(m)
         assert m.tolist() == [float(world), 10.0, 3.0]
-        assert (hx.lo is None) == (rank == 0) and (hx.hi is None) == (rank == world - 1)
+        assert a.periodic_z or ((hx.lo is None) == (rank == 0) and (hx.hi is None) == (rank == world - 1))
         dist.barrier()
         if rank == 0:
             print("SLAB_CHECK_OK cpu world=%d case=%s" % (world, a.case))
@@ -116,10 +129,15 @@ def main():
             eng.set_state(Um, Tm)
             st = SlabStepper(eng, mine.bc, rank, world, dev, overlap=overlap)
             st.startup()
-            st.steps(a.steps)
+            if overlap:
+                done, _, err = st.run(a.steps)          # the polling loop of the C++ driver (xf_slab_run)
+                assert (done, err) == (a.steps, 0)
+            else:
+                st.steps(a.steps)
             assert not st.any_error()
             torch.cuda.synchronize()
             results[overlap] = (eng.download(eng.U).reshape(mine.block.Zmax, plane), eng.time()[0])
+            st.close()
         eng.close()
     assert np.array_equal(results[False][0], results[True][0]), "overlapped exchange changed the result"
     # host-buffer step (bench e2e on N > 1): the chunked, overlapped form against upload -> step -> download, 2 steps each
@@ -142,10 +160,12 @@ def main():
                         st.step()
                         hb = np.ascontiguousarray(eng.download(eng.U))
                     else:
-                        assert st.step_host(hb.ctypes.data), "overlapped host step not available"
+                        applied, herr = st.step_host(hb.ctypes.data)
+                        assert applied and herr == 0, "overlapped host step not available"
                 assert not st.any_error()
                 torch.cuda.synchronize()
                 hres[mode] = (hb.copy(), eng.time()[0])
+                st.close()
             eng.close()
         assert hres["plain"][1] == hres["overlapped"][1], "host-step time differs"
         assert np.array_equal(hres["plain"][0], hres["overlapped"][0]), "overlapped host step differs from upload/step/download"

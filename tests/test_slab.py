@@ -36,11 +36,20 @@ def test_exchange_protocol_gloo(world, case, strong):
     _launch(world, ["--mode", "cpu", "--case", case] + (["--strong"] if strong else []))
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_protocol_periodic_z_gloo(world):
+    """Periodic z boundary: the outer faces of the first and last rank exchange with each other; on two ranks both neighbours are the
+    same peer and the posting order decides which ghosts a message lands in."""
+    _launch(world, ["--mode", "cpu", "--case", "sbi", "--periodic-z"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,strong,weno,pp,alpha", [("sbi", False, 5, 0, "LLF"), ("jet", True, 5, 0, "LLF"), ("sbi", False, 6, 1, "LLF"), ("sbi", False, 7, 0, "ROE"),
-                                                       ("sbi", False, 5, 0, "GLF"), ("jet", True, 6, 0, "GLF")])
+                                                       ("sbi", False, 5, 0, "GLF"), ("jet", True, 6, 0, "GLF"), ("sbi-periodic", False, 5, 0, "LLF")])
 def test_two_slabs_equal_one_block_bitwise(case, strong, weno, pp, alpha):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    _launch(2, ["--mode", "gpu", "--case", case, "--steps", "5", "--weno", str(weno), "--pp", str(pp), "--alpha", alpha] + (["--strong"] if strong else []))
+    per = case.endswith("-periodic")
+    _launch(2, ["--mode", "gpu", "--case", case.split("-")[0], "--steps", "5", "--weno", str(weno), "--pp", str(pp), "--alpha", alpha] + (["--strong"] if strong else [])
+            + (["--periodic-z"] if per else []))

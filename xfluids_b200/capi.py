@@ -76,11 +76,11 @@ _PROTOS = {
     "xf_halo_unpack": (C.c_int, [_P, _P, C.c_int, _P]),
     "xf_halo_pack_on": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "xf_halo_unpack_on": (C.c_int, [_P, _P, C.c_int, _P, _P]),
-    "xf_stage_interior": (C.c_int, [_P, _P, _P, C.c_int]),
+    "xf_stage_interior": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_stage_finish": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "xf_step_host": (C.c_int, [_P, _P, _BC, C.c_int, C.c_double, _P, _P, _P, _IP, _IP]),
     "xf_set_host_overlap": (C.c_int, [_P, C.c_int]),
-    "xf_host_begin": (C.c_int, [_P, _P, _BC, C.c_double, _P, _P]),
+    "xf_host_begin": (C.c_int, [_P, _P, _BC, C.c_double, _P, _P, _P]),
     "xf_host_stage1_finish": (C.c_int, [_P, _BC, _P, _P, _P]),
     "xf_host_stage3": (C.c_int, [_P, _P, _P, _P, _P, _IP]),
     "xf_host_alloc_pinned": (_P, [C.c_size_t]),
@@ -89,6 +89,27 @@ _PROTOS = {
     "xf_profile_step": (C.c_int, [_P, _P, _P, _P, _BC, C.c_double, C.c_float * 8]),
     "xf_measure_peaks": (C.c_int, [C.c_int, _DP, _DP]),
     "xf_log_eval": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
+    "xf_measure_pcie": (C.c_int, [_P, _P, C.c_size_t, _DP, _DP]),
+    "xf_slab_last_error": (C.c_char_p, []),
+    "xf_comm_unique_id": (C.c_int, [C.c_char * 128]),
+    "xf_comm_create": (C.c_int, [C.c_char * 128, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "xf_comm_destroy": (C.c_int, [_P]),
+    "xf_comm_rank": (C.c_int, [_P]),
+    "xf_comm_world": (C.c_int, [_P]),
+    "xf_comm_allreduce_max": (C.c_int, [_P, _P, C.c_int, _P]),
+    "xf_comm_allreduce_max_int": (C.c_int, [_P, _P, C.c_int, _P]),
+    "xf_slab_create": (C.c_int, [_P, _P, _BC, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "xf_slab_destroy": (C.c_int, [_P]),
+    "xf_slab_set_overlap": (C.c_int, [_P, C.c_int]),
+    "xf_slab_neighbours": (C.c_int, [_P, C.c_int * 2]),
+    "xf_slab_halo": (C.c_int, [_P, _P]),
+    "xf_slab_startup": (C.c_int, [_P, _P, _IP]),
+    "xf_slab_stage": (C.c_int, [_P, _P, _P, _P, C.c_int]),
+    "xf_slab_step": (C.c_int, [_P, _P, _P, _P, C.c_double]),
+    "xf_slab_run": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, _IP, _DP, _IP]),
+    "xf_slab_any_error": (C.c_int, [_P, _IP]),
+    "xf_slab_step_host": (C.c_int, [_P, _P, C.c_double, _P, _P, _P, _IP]),
+    "xf_slab_allreduce_max_host": (C.c_int, [_P, _DP, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = sorted(_PROTOS)
@@ -118,7 +139,8 @@ class Lib:
     def check(self, rc, allow_numeric=False):
         if rc == 0 or (allow_numeric and rc == -3):
             return rc
-        raise XfError("xfluids_b200 error %d: %s" % (rc, (self.dll.xf_last_error() or b"").decode()))
+        msg = (self.dll.xf_slab_last_error() if rc == -4 else self.dll.xf_last_error()) or b""
+        raise XfError("xfluids_b200 error %d: %s" % (rc, msg.decode() or (self.dll.xf_slab_last_error() or b"").decode()))
 
 
 def _dptr(a):
@@ -224,7 +246,7 @@ class Engine:
         self.L.check(self.L.dll.xf_rk_stage(self.ctx, self.U, self.U1, self.LU, b, flag))
 
     def stage_interior(self, flag):
-        self.L.check(self.L.dll.xf_stage_interior(self.ctx, self.U, self.U1, flag))
+        self.L.check(self.L.dll.xf_stage_interior(self.ctx, self.U, self.U1, self.LU, flag))
 
     def stage_finish(self, flag):
         self.L.check(self.L.dll.xf_stage_finish(self.ctx, self.U, self.U1, self.LU, flag))

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/xfluids_b200.h"
 #include "xf_launch.h"
@@ -47,16 +49,18 @@ struct XfTable
 	decltype(&xf_strict::launch_layout) layout;
 	decltype(&xf_strict::launch_scalar_pad) scalar_pad;
 	decltype(&xf_strict::launch_halo) halo;
+	decltype(&xf_strict::launch_sweep_x) sweep_x;
+	decltype(&xf_strict::launch_march) march;
 };
 static const XfTable T_STRICT = {xf_strict::launch_prim, xf_strict::launch_sweeps, xf_strict::launch_lu, xf_strict::launch_rk, xf_strict::launch_nan,
 								 xf_strict::launch_bc, xf_strict::launch_dt, xf_strict::launch_dt_final, xf_strict::launch_layout,
-								 xf_strict::launch_scalar_pad, xf_strict::launch_halo};
+								 xf_strict::launch_scalar_pad, xf_strict::launch_halo, xf_strict::launch_sweep_x, xf_strict::launch_march};
 // fast mode: FMA contraction in the sweeps / LU / RK only.  Primitive recovery stays strict: its Newton loop stops on an
 // absolute tolerance and is capped/limited, so a 1-ulp difference can change the trip count and move T by O(1e-6)
 // (measured: 2e-6 relative on U after one jet step with a contracted prim kernel).
 static const XfTable T_FAST = {xf_strict::launch_prim, xf_fast::launch_sweeps, xf_fast::launch_lu, xf_fast::launch_rk, xf_fast::launch_nan,
 							   xf_fast::launch_bc, xf_fast::launch_dt, xf_fast::launch_dt_final, xf_fast::launch_layout,
-							   xf_fast::launch_scalar_pad, xf_fast::launch_halo};
+							   xf_fast::launch_scalar_pad, xf_fast::launch_halo, xf_fast::launch_sweep_x, xf_fast::launch_march};
 
 struct xf_ctx
 {
@@ -83,6 +87,12 @@ struct xf_ctx
 	int gbc[6] = {-1, -1, -1, -1, -1, -1};
 	double gt_end = 0;
 	long long glaunches = 0; // kernel launches inside one replay
+	// TMA tensor maps of the marching sweeps: per (sweep input field, direction); the primitive / Y maps are per direction
+	std::map<std::pair<const void *, int>, XfTma> tma;
+	// 1 (default): tiled y / z sweeps store the wall fluxes, one kernel forms the divergence and the stage update.  0 (XF_MARCH=1): the
+	// TMA-fed marching sweeps with the divergence / update fused in (xf_march.cuh) -- bit-identical results, measured slower on every
+	// BASELINE config (profiles/r02_tuning.md), kept selectable for that A/B
+	int tiled = 1;
 	size_t ncells() const { return size_t(bl.Xmax) * bl.Ymax * bl.Zmax; }
 };
 
@@ -123,6 +133,7 @@ __global__ void __launch_bounds__(256) k_log_eval(const double *__restrict__ x, 
 
 extern "C"
 {
+	static int ensure_fw(xf_ctx *c);
 	const char *xf_last_error(void) { return g_err.c_str(); }
 
 	// y[i] = xf_log(x[i]) evaluated on `device` (host arrays): the parity test of the device logarithm against the host libm
@@ -204,42 +215,54 @@ extern "C"
 			}
 		}
 		const size_t N = (size_t)d.N;
+		const char *march = std::getenv("XF_MARCH");
+		c->tiled = (march && march[0] == '1') ? 0 : 1;
+		// every failure from here on goes through one exit that releases what has been allocated; the first failure wins
 		int rc = 0;
-		double **sc_arr[] = {&d.u, &d.v, &d.w, &d.p, &d.H, &d.c, &d.T};
-		for (double **p : sc_arr)
-			rc |= dmalloc(c, p, N);
+		auto alloc = [&](double **p, size_t n)
+		{ if (!rc) rc = dmalloc(c, p, n); };
+		if (cudaDeviceGetAttribute(&d.nsm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+			rc = fail(XF_ERR_CUDA, "cudaDeviceGetAttribute");
+		if (c->cop && N >= (size_t)0xffffffffu)
+			rc = fail(XF_ERR_ARG, "block too large for 32-bit cell indices");
+		double *prim5 = nullptr; // u, v, w, p, c contiguous: one 4-D TMA tensor map covers them (xf_march.cuh)
+		alloc(&prim5, 5 * N);
+		d.u = prim5, d.v = prim5 + N, d.w = prim5 + 2 * N, d.p = prim5 + 3 * N, d.c = prim5 + 4 * N;
+		alloc(&d.H, N), alloc(&d.T, N);
 		if (c->cop)
 		{
 			double **cop_arr[] = {&d.g3, &d.dpdrho, &d.e, &d.prho};
 			for (double **p : cop_arr)
-				rc |= dmalloc(c, p, N);
-			rc |= dmalloc(c, &d.y, N * c->ns);
-			rc |= dmalloc(c, &d.dpdrhoi, N * (c->ns - 1));
+				alloc(p, N);
+			alloc(&d.y, N * c->ns);
+			alloc(&d.dpdrhoi, N * (c->ns - 1));
 		}
-		for (int dir = 0; dir < 3; dir++)
-			if ((dir == 0 && d.DimX) || (dir == 1 && d.DimY) || (dir == 2 && d.DimZ))
-				rc |= dmalloc(c, &d.Fw[dir], N * c->E);
-		rc |= dmalloc(c, &d.red, XF_RED_COUNT);
+		alloc(&d.red, XF_RED_COUNT);
 		double *errp = nullptr;
-		rc |= dmalloc(c, &errp, 2);
+		alloc(&errp, 2);
 		d.err = reinterpret_cast<int *>(errp);
 		if (c->cop)
 		{ // hard-cell list of the two-pass primitive recovery: one 32-bit index per cell at most, + the counter
-			if (N >= (size_t)0xffffffffu)
-				return fail(XF_ERR_ARG, "block too large for 32-bit cell indices");
 			double *hp = nullptr;
-			rc |= dmalloc(c, &hp, N / 2 + 2);
+			alloc(&hp, N / 2 + 2);
 			d.hard_count = reinterpret_cast<unsigned *>(hp);
 			d.hard_ids = d.hard_count + 2;
 		}
+		if (!rc && c->tiled)
+			rc = ensure_fw(c);
+		if (!rc && cudaMallocHost((void **)&c->h_pin, 16 * sizeof(double)) != cudaSuccess)
+			rc = fail(XF_ERR_CUDA, "cudaMallocHost");
+		if (!rc && cudaMallocHost((void **)&c->h_err, 4 * sizeof(int)) != cudaSuccess)
+			rc = fail(XF_ERR_CUDA, "cudaMallocHost");
+		if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess)
+			rc = fail(XF_ERR_CUDA, "cudaStreamSynchronize");
 		if (rc)
 		{
+			const std::string keep = g_err;
 			xf_destroy(c);
+			g_err = keep;
 			return rc;
 		}
-		CU(cudaMallocHost((void **)&c->h_pin, 16 * sizeof(double)));
-		CU(cudaMallocHost((void **)&c->h_err, 4 * sizeof(int)));
-		CU(cudaStreamSynchronize(c->stream));
 		*out = c;
 		return XF_OK;
 	}
@@ -397,6 +420,193 @@ extern "C"
 		return XF_OK;
 	}
 	static int update_states(xf_ctx *c, double *U, bool gather_dt) { return update_states_range(c, U, gather_dt, true, 0, c->d.Zmax); }
+
+	// ---- wall-flux fields of the block-level API (FluxFw / Gw / Hw): allocated on first use, the fused path never stores wall fluxes ----
+	static int ensure_fw(xf_ctx *c)
+	{
+		XfDev &d = c->d;
+		for (int dir = 0; dir < 3; dir++)
+			if (((dir == 0 && d.DimX) || (dir == 1 && d.DimY) || (dir == 2 && d.DimZ)) && !d.Fw[dir])
+			{
+				int rc = dmalloc(c, &d.Fw[dir], (size_t)d.N * c->E);
+				if (rc)
+					return rc;
+				if (c->gexec) // XfDev travels by value inside captured launches
+					cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+			}
+		return 0;
+	}
+
+	// ---- TMA tensor maps of the marching sweeps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
+	typedef CUresult (*xf_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+									 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static xf_encode_fn tma_encoder()
+	{
+		static xf_encode_fn fn = nullptr;
+		if (!fn)
+		{
+			void *p = nullptr;
+			cudaDriverEntryPointQueryResult q;
+			if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+				fn = (xf_encode_fn)p;
+		}
+		return fn;
+	}
+	// [ncomp][Zmax][Ymax][Xp] doubles at `base` as a 4-D tensor (x, y, z, component); box = XF_MW cells in x by TF cells along `dir`
+	static int make_map(xf_ctx *c, CUtensorMap *m, const double *base, int ncomp, int dir, int rows = 0, int width = XF_MW)
+	{
+		const XfDev &d = c->d;
+		xf_encode_fn enc = tma_encoder();
+		if (!enc)
+			return fail(XF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+		const cuuint32_t TF = rows > 0 ? (cuuint32_t)rows : (cuuint32_t)XF_MTF(d.weno);
+		const cuuint64_t gdim[4] = {(cuuint64_t)d.Xp, (cuuint64_t)d.Ymax, (cuuint64_t)d.Zmax, (cuuint64_t)ncomp};
+		const cuuint64_t gstr[3] = {(cuuint64_t)d.Xp * 8, (cuuint64_t)d.sZ * 8, (cuuint64_t)d.N * 8};
+		const cuuint32_t box[4] = {(cuuint32_t)width, dir == 1 ? TF : 1u, dir == 2 ? TF : 1u, (cuuint32_t)ncomp};
+		const cuuint32_t es[4] = {1, 1, 1, 1};
+		const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+							   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS)
+			return fail(XF_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+		return 0;
+	}
+	static int tma_for(xf_ctx *c, const double *UI, int dir, const XfTma **out)
+	{
+		const auto key = std::make_pair((const void *)UI, dir);
+		auto it = c->tma.find(key);
+		if (it == c->tma.end())
+		{
+			XfTma t;
+			std::memset(&t, 0, sizeof(t));
+			int rc;
+			if ((rc = make_map(c, &t.U, UI, c->E, dir)) || (rc = make_map(c, &t.P, c->d.u, 5, dir)))
+				return rc;
+			if (c->cop && (rc = make_map(c, &t.Y, c->d.y, c->ns - 1, dir)))
+				return rc;
+			it = c->tma.emplace(key, t).first;
+		}
+		*out = &it->second;
+		return 0;
+	}
+
+	// the conserved pencil of one tile of the tiled y / z sweeps: XF_TW_ cells x XF_TILE_ROWS rows x Emax components (cache key: dir + 8)
+	static int tile_map_for(xf_ctx *c, const double *UI, int dir, const CUtensorMap **out)
+	{
+		const auto key = std::make_pair((const void *)UI, dir + 8);
+		auto it = c->tma.find(key);
+		if (it == c->tma.end())
+		{
+			XfTma t;
+			std::memset(&t, 0, sizeof(t));
+			int rc;
+			if ((rc = make_map(c, &t.U, UI, c->E, dir, XF_TILE_ROWS(c->d.weno), XF_TW_)))
+				return rc;
+			it = c->tma.emplace(key, t).first;
+		}
+		*out = &it->second.U;
+		return 0;
+	}
+	// tiled sweeps of `dirmask` (wall fluxes stored in Fw)
+	static int tiled_sweeps(xf_ctx *c, const double *UI, int dirmask, int kp0, int kp1, int tz0, int tz1)
+	{
+		const CUtensorMap *tmy = nullptr, *tmz = nullptr;
+		int rc;
+		if ((dirmask & 2) && c->d.DimY && (rc = tile_map_for(c, UI, 1, &tmy)))
+			return rc;
+		if ((dirmask & 4) && c->d.DimZ && (rc = tile_map_for(c, UI, 2, &tmz)))
+			return rc;
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz));
+		return XF_OK;
+	}
+
+	// A march shorter than a few waves of blocks (2-D grids: one column per XF_MW cells of x) is cut into segments along the sweep; each
+	// segment restages NST - 1 rows and recomputes one seed face.  Segment length = m TF - 1 cells, i.e. m full iterations of faces.
+	static void plan_segments(const xf_ctx *c, int ntr, int len, XfMarchArgs *a)
+	{
+		const XfDev &d = c->d;
+		const int TF = XF_MTF(d.weno);
+		const long long cols = (long long)((d.Xi + XF_MW - 1) / XF_MW) * ntr, target = 4LL * d.nsm;
+		a->nseg = 1, a->seglen = len;
+		if (cols >= target || len < 8 * TF)
+			return;
+		long long want = (target + cols - 1) / cols;
+		if (want > len / (4 * TF))
+			want = len / (4 * TF);
+		if (want <= 1)
+			return;
+		const int m = (int)((len / want + 1 + TF - 1) / TF);
+		a->seglen = m * TF - 1;
+		a->nseg = (len + a->seglen - 1) / a->seglen;
+	}
+
+	// The sweeps of one RK stage.  dirmask: the directions to run in this call; the x and y sweeps cover the z-planes [kp0, kp1), the z
+	// sweep the cells (planes) [ka, kb) (absolute indices; < 0: all inner planes).  Every direction adds its part of the divergence to LU in
+	// the reference's x -> y -> z order (UpdateFluidLU, Reconstruction_kernels.hpp:201-234); with `finish` the last active direction goes on
+	// to the NaN guard and the stage update in the same kernel, and neither wall fluxes nor LU reach HBM.
+	static int stage_sweeps(xf_ctx *c, double *U, double *U1, double *LU, int flag, int dirmask, int kp0, int kp1, int ka, int kb, bool finish)
+	{
+		const XfDev &d = c->d;
+		double *UI = flag == 1 ? U : U1;
+		const bool allz = ka < 0;
+		if (kp0 < 0)
+			kp0 = d.Bz, kp1 = d.Bz + d.Zi;
+		if (ka < 0)
+			ka = d.Bz, kb = d.Bz + d.Zi;
+		if (c->tiled)
+		{ // round-1 path: tiled sweeps store the wall fluxes, one kernel forms the divergence and the update
+			if (!allz)
+				return fail(XF_ERR_ARG, "the tiled sweeps cover whole blocks in z only");
+			int rc;
+			if ((rc = tiled_sweeps(c, UI, dirmask, kp0, kp1, -1, -1)))
+				return rc;
+			if (finish)
+			{
+				KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
+				c->launches++;
+			}
+			return XF_OK;
+		}
+		const int first_dir = d.DimX ? 0 : (d.DimY ? 1 : 2), last_dir = d.DimZ ? 2 : (d.DimY ? 1 : 0);
+		XfMarchArgs a;
+		std::memset(&a, 0, sizeof(a));
+		a.flag = flag, a.guard = 1, a.U = U, a.U1 = U1, a.LU = LU, a.dt_dev = d.red + XF_RED_DT, a.nseg = 1;
+		bool rk_pass = false;
+		int rc;
+		if ((dirmask & 1) && d.DimX)
+		{
+			a.mode = XF_MODE_ACC, a.first = 1, a.t0 = kp0, a.t1 = kp1;
+			KL(c->t->sweep_x(d, c->ns, c->cop, UI, a, c->stream));
+			c->launches++;
+			rk_pass = finish && last_dir == 0; // 1-D: the chunks of the x sweep overlap, no in-place update there
+		}
+		if ((dirmask & 2) && d.DimY)
+		{
+			const XfTma *tm;
+			if ((rc = tma_for(c, UI, 1, &tm)))
+				return rc;
+			a.mode = (finish && last_dir == 1) ? XF_MODE_RK : XF_MODE_ACC, a.first = first_dir == 1, a.t0 = kp0, a.t1 = kp1, a.ca = d.By, a.cb = d.By + d.Yi;
+			plan_segments(c, kp1 - kp0, d.Yi, &a);
+			if (a.mode == XF_MODE_RK && a.nseg > 1 && flag == 2)
+				a.mode = XF_MODE_ACC, rk_pass = true; // stage 2 updates its own input: not across segment boundaries (xf_march.cuh)
+			KL(c->t->march(d, c->ns, c->cop, *tm, UI, a, 1, c->stream));
+			c->launches++;
+		}
+		if ((dirmask & 4) && d.DimZ)
+		{
+			const XfTma *tm;
+			if ((rc = tma_for(c, UI, 2, &tm)))
+				return rc;
+			a.mode = finish ? XF_MODE_RK : XF_MODE_ACC, a.first = first_dir == 2, a.t0 = d.By, a.t1 = d.By + d.Yi, a.ca = ka, a.cb = kb, a.nseg = 1, a.seglen = kb - ka;
+			KL(c->t->march(d, c->ns, c->cop, *tm, UI, a, 2, c->stream));
+			c->launches++;
+		}
+		if (rk_pass)
+		{
+			KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, flag, 1, 0, c->stream, -1, -1));
+			c->launches++;
+		}
+		return XF_OK;
+	}
 	int xf_error_flags(xf_ctx *c, int flags[4])
 	{
 		CU(cudaMemcpyAsync(c->h_err, c->d.err, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -426,7 +636,47 @@ extern "C"
 	}
 	int xf_get_lu(xf_ctx *c, const double *U, double *LU)
 	{
-		KL(c->t->sweeps(c->d, c->ns, c->cop, U, c->stream, &c->launches, 7, -1, -1, -1, -1));
+		// block-level form: the wall fluxes of the three directions are stored (the reference's FluxFw / Gw / Hw, readable through
+		// xf_get_wallflux_aos), then UpdateFluidLU forms the divergence
+		int rc;
+		if ((rc = ensure_fw(c)))
+			return rc;
+		const XfDev &d = c->d;
+		if (c->tiled)
+		{
+			if ((rc = tiled_sweeps(c, U, 7, -1, -1, -1, -1)))
+				return rc;
+		}
+		else
+		{
+			XfMarchArgs a;
+			std::memset(&a, 0, sizeof(a));
+			a.mode = XF_MODE_FW, a.nseg = 1, a.t0 = d.Bz, a.t1 = d.Bz + d.Zi;
+			if (d.DimX)
+			{
+				KL(c->t->sweep_x(d, c->ns, c->cop, U, a, c->stream));
+				c->launches++;
+			}
+			if (d.DimY)
+			{
+				const XfTma *tm;
+				if ((rc = tma_for(c, U, 1, &tm)))
+					return rc;
+				a.Fw = d.Fw[1], a.ca = d.By, a.cb = d.By + d.Yi;
+				plan_segments(c, d.Zi, d.Yi, &a);
+				KL(c->t->march(d, c->ns, c->cop, *tm, U, a, 1, c->stream));
+				c->launches++;
+			}
+			if (d.DimZ)
+			{
+				const XfTma *tm;
+				if ((rc = tma_for(c, U, 2, &tm)))
+					return rc;
+				a.Fw = d.Fw[2], a.t0 = d.By, a.t1 = d.By + d.Yi, a.ca = d.Bz, a.cb = d.Bz + d.Zi, a.nseg = 1, a.seglen = d.Zi;
+				KL(c->t->march(d, c->ns, c->cop, *tm, U, a, 2, c->stream));
+				c->launches++;
+			}
+		}
 		KL(c->t->lu(c->d, c->E, LU, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -492,14 +742,11 @@ extern "C"
 		// by the last UpdateStates) -> gather the maxima there
 		if ((rc = update_states(c, UI, flag == 3)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 7, -1, -1, -1, -1));
-		// flux divergence + NaN guard + RK update in one kernel; LU stays in registers
-		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
-		c->launches++;
-		return XF_OK;
+		// x, y sweeps accumulate their part of the divergence in LU; the last direction adds its own and applies NaN guard + RK update
+		return stage_sweeps(c, U, U1, LU, flag, 7, -1, -1, -1, -1, true);
 	}
 	// ---- one stage split around the z-halo exchange (multi-GPU overlap; include/xfluids_b200.h) --------------
-	int xf_stage_interior(xf_ctx *c, double *U, double *U1, int flag)
+	int xf_stage_interior(xf_ctx *c, double *U, double *U1, double *LU, int flag)
 	{
 		if (flag < 1 || flag > 3 || !c->d.DimZ)
 			return fail(XF_ERR_ARG, "xf_stage_interior: flag 1..3 and an active z dimension");
@@ -507,8 +754,7 @@ extern "C"
 		int rc;
 		if ((rc = update_states_range(c, UI, flag == 3, true, c->d.Bz, c->d.Zmax - c->d.Bz)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 3, -1, -1, -1, -1));
-		return XF_OK;
+		return stage_sweeps(c, U, U1, LU, flag, 3, -1, -1, -1, -1, false);
 	}
 	int xf_stage_finish(xf_ctx *c, double *U, double *U1, double *LU, int flag)
 	{
@@ -520,10 +766,7 @@ extern "C"
 			return rc;
 		if ((rc = update_states_range(c, UI, flag == 3, false, c->d.Zmax - c->d.Bz, c->d.Zmax)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 4, -1, -1, -1, -1));
-		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
-		c->launches++;
-		return XF_OK;
+		return stage_sweeps(c, U, U1, LU, flag, 4, -1, -1, -1, -1, true);
 	}
 	// ---- one stage split between primitive recovery and sweeps (multi-GPU GLF: the 9 running maxima of |lambda| are MAX-reduced over
 	//      the ranks in between, like the reference's MPI build does for eigen_block) ----------------------------------------------
@@ -537,10 +780,7 @@ extern "C"
 	{
 		if (flag < 1 || flag > 3)
 			return fail(XF_ERR_ARG, "flag must be 1..3");
-		KL(c->t->sweeps(c->d, c->ns, c->cop, flag == 1 ? U : U1, c->stream, &c->launches, 7, -1, -1, -1, -1));
-		KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
-		c->launches++;
-		return XF_OK;
+		return stage_sweeps(c, U, U1, LU, flag, 7, -1, -1, -1, -1, true);
 	}
 	int xf_get_time(xf_ctx *c, double *time, double *last_dt)
 	{
@@ -664,14 +904,19 @@ extern "C"
 			CU(cudaEventRecord(ev[e++], c->stream));
 			if ((rc = update_states(c, UI, flag == 3)))
 				return rc;
+			const int last_dir = c->d.DimZ ? 2 : (c->d.DimY ? 1 : 0);
 			for (int dir = 0; dir < 3; dir++)
 			{
 				CU(cudaEventRecord(ev[e++], c->stream));
-				KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, 1 << dir, -1, -1, -1, -1));
+				if ((rc = c->tiled ? tiled_sweeps(c, UI, 1 << dir, -1, -1, -1, -1) : stage_sweeps(c, U, U1, LU, flag, 1 << dir, -1, -1, -1, -1, dir == last_dir)))
+					return rc;
 			}
 			CU(cudaEventRecord(ev[e++], c->stream));
-			KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
-			c->launches++;
+			if (c->tiled)
+			{
+				KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
+				c->launches++;
+			}
 		}
 		CU(cudaEventRecord(ev[e++], c->stream));
 		CU(cudaStreamSynchronize(c->stream));
@@ -748,6 +993,41 @@ extern "C"
 		return XF_OK;
 	}
 
+	// achieved host <-> device copy rates (GB/s) of this context's device for `bytes` of pinned host memory, through the AoS staging
+	// buffer: the denominators of the end-to-end leg (what the PCIe link of this rank delivers when nothing else runs)
+	int xf_measure_pcie(xf_ctx *c, void *h_pinned, size_t bytes, double *h2d_gbs, double *d2h_gbs)
+	{
+		CU(cudaSetDevice(c->device));
+		if (ensure_stage(c))
+			return XF_ERR_CUDA;
+		const size_t cap = c->ncells() * c->E * sizeof(double);
+		if (bytes > cap)
+			bytes = cap;
+		cudaEvent_t a, b;
+		CU(cudaEventCreate(&a));
+		CU(cudaEventCreate(&b));
+		float ms = 0;
+		int rc = XF_OK;
+		for (int dir = 0; dir < 2 && rc == XF_OK; dir++)
+		{
+			cudaError_t e = cudaEventRecord(a, c->stream);
+			if (e == cudaSuccess)
+				e = dir == 0 ? cudaMemcpyAsync(c->stage, h_pinned, bytes, cudaMemcpyHostToDevice, c->stream) : cudaMemcpyAsync(h_pinned, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess)
+				e = cudaEventRecord(b, c->stream);
+			if (e == cudaSuccess)
+				e = cudaEventSynchronize(b);
+			if (e == cudaSuccess)
+				e = cudaEventElapsedTime(&ms, a, b);
+			if (e != cudaSuccess)
+				rc = fail(XF_ERR_CUDA, std::string("xf_measure_pcie: ") + cudaGetErrorString(e));
+			else
+				*(dir == 0 ? h2d_gbs : d2h_gbs) = bytes / (ms * 1e-3) / 1e9;
+		}
+		cudaEventDestroy(a), cudaEventDestroy(b);
+		return rc;
+	}
+
 	// ---- halo -----------------------------------------------------------------------------------
 	size_t xf_halo_doubles(const xf_ctx *c) { return (size_t)c->E * c->d.Bz * (size_t)c->d.sZ; }
 	int xf_halo_pack_on(xf_ctx *c, const double *U, int face, double *buf, void *stream)
@@ -813,7 +1093,7 @@ extern "C"
 		const XfDev &d = c->d;
 		return c->host_chunks > 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks && c->sc.artificial_type != 3;
 	}
-	int xf_host_begin(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1)
+	int xf_host_begin(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU)
 	{
 		if (!host_overlap_ok(c))
 			return fail(XF_ERR_ARG, "xf_host_begin: needs a 3-D block, host_chunks > 1 and ROE / LLF splitting");
@@ -859,7 +1139,8 @@ extern "C"
 			{
 				if ((rc = update_states_range(c, U, false, false, p0, p1)))
 					return rc;
-				KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, p0, p1, -1, -1));
+				if ((rc = stage_sweeps(c, U, U1, LU, 1, 3, p0, p1, -1, -1, false)))
+					return rc;
 			}
 		}
 		return XF_OK;
@@ -873,12 +1154,9 @@ extern "C"
 		KL(c->t->bc(d, c->E, c->cop, U, bc, c->stream, &c->launches, 4, -1, -1));
 		if ((rc = update_states_range(c, U, false, false, 0, lo)) || (rc = update_states_range(c, U, false, false, hi, Zmax)))
 			return rc;
-		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, Bz, lo, -1, -1));
-		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 3, hi, Zmax - Bz, -1, -1));
-		KL(c->t->sweeps(d, c->ns, c->cop, U, c->stream, &c->launches, 4, -1, -1, -1, -1));
-		KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 1, 1, 1, c->stream, -1, -1));
-		c->launches++;
-		return XF_OK;
+		if ((rc = stage_sweeps(c, U, U1, LU, 1, 3, Bz, lo, -1, -1, false)) || (rc = stage_sweeps(c, U, U1, LU, 1, 3, hi, Zmax - Bz, -1, -1, false)))
+			return rc;
+		return stage_sweeps(c, U, U1, LU, 1, 4, -1, -1, -1, -1, true);
 	}
 	int xf_host_stage3(xf_ctx *c, double *h_U, double *U, double *U1, double *LU, int *error)
 	{
@@ -893,8 +1171,13 @@ extern "C"
 		// now known, the SoA->AoS conversion of those planes and their copy to the host on the copy stream.
 		if ((rc = update_states(c, U1, true)))
 			return rc;
-		const int TF = xf_strict::z_tile_faces(), ntz = xf_strict::xf_z_tiles(d), Zi = d.Zi;
-		const int nd = nch < ntz ? nch : ntz;
+		// chunks of inner planes.  Tiled sweeps: whole z tiles (TF faces each); the planes [ka, kb) whose two z faces are known after tiles
+		// < t1 are updated.  Marching sweeps: the cells one segment of the march updates, m TF - 1 planes (m full iterations of faces,
+		// the first face only seeds the divergence).
+		const int TF = c->tiled ? xf_strict::z_tile_faces() : XF_MTF(d.weno), Zi = d.Zi, ntz = xf_strict::xf_z_tiles(d);
+		int clen = ((Zi + nch - 1) / nch + 1 + TF - 1) / TF * TF - 1;
+		clen = clen < TF - 1 ? TF - 1 : clen;
+		const int nd = c->tiled ? (nch < ntz ? nch : ntz) : (Zi + clen - 1) / clen;
 		if ((int)c->chunk_ev.size() < nch + 1 + nd)
 		{
 			const size_t old = c->chunk_ev.size();
@@ -904,16 +1187,28 @@ extern "C"
 		}
 		for (int ch = 0; ch < nd; ch++)
 		{
-			const int t0 = (int)((long long)ntz * ch / nd), t1 = (int)((long long)ntz * (ch + 1) / nd);
-			// tiles [t0, t1) = z faces Bz - 1 + TF t0 .. Bz - 2 + TF t1  ->  inner planes (0-based) [ka, kb) have both faces
-			int ka = TF * t0 - 1, kb = TF * t1 - 1;
-			ka = ka < 0 ? 0 : ka, kb = kb > Zi ? Zi : kb;
-			if (ch == nd - 1)
-				kb = Zi;
-			KL(c->t->sweeps(d, c->ns, c->cop, U1, c->stream, &c->launches, 3, Bz + ka, Bz + kb, -1, -1));
-			KL(c->t->sweeps(d, c->ns, c->cop, U1, c->stream, &c->launches, 4, -1, -1, t0, t1));
-			KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 3, 1, 1, c->stream, ka, kb));
-			c->launches++;
+			int ka, kb; // inner planes (0-based) [ka, kb) this chunk updates
+			if (c->tiled)
+			{
+				const int t0 = (int)((long long)ntz * ch / nd), t1 = (int)((long long)ntz * (ch + 1) / nd);
+				// tiles [t0, t1) = z faces Bz - 1 + TF t0 .. Bz - 2 + TF t1
+				ka = TF * t0 - 1, kb = TF * t1 - 1;
+				ka = ka < 0 ? 0 : ka, kb = kb > Zi ? Zi : kb;
+				if (ch == nd - 1)
+					kb = Zi;
+				if ((rc = tiled_sweeps(c, U1, 3, Bz + ka, Bz + kb, -1, -1)))
+					return rc;
+				if ((rc = tiled_sweeps(c, U1, 4, -1, -1, t0, t1)))
+					return rc;
+				KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, 3, 1, 1, c->stream, ka, kb));
+				c->launches++;
+			}
+			else
+			{
+				ka = ch * clen, kb = (ch + 1) * clen < Zi ? (ch + 1) * clen : Zi;
+				if ((rc = stage_sweeps(c, U, U1, LU, 3, 3, Bz + ka, Bz + kb, -1, -1, false)) || (rc = stage_sweeps(c, U, U1, LU, 3, 4, -1, -1, Bz + ka, Bz + kb, true)))
+					return rc;
+			}
 			// planes to ship: the updated inner planes, plus the z ghost planes with the first / last chunk
 			const int z0 = ch == 0 ? 0 : Bz + ka, z1 = ch == nd - 1 ? Zmax : Bz + kb;
 			KL(c->t->layout(d, c->E, U, c->stage, 0, c->stream, (long long)z0 * d.Ymax, (long long)(z1 - z0) * d.Ymax));
@@ -934,7 +1229,7 @@ extern "C"
 	static int step_host_overlapped(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU, int *steps_done, int *error)
 	{
 		int rc;
-		if ((rc = xf_host_begin(c, h_U, bc, t_end, U, U1)) || (rc = xf_host_stage1_finish(c, bc, U, U1, LU)) || (rc = xf_rk_stage(c, U, U1, LU, bc, 2)) ||
+		if ((rc = xf_host_begin(c, h_U, bc, t_end, U, U1, LU)) || (rc = xf_host_stage1_finish(c, bc, U, U1, LU)) || (rc = xf_rk_stage(c, U, U1, LU, bc, 2)) ||
 			(rc = xf_boundary(c, U1, bc)))
 			return rc;
 		if (steps_done)

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include "xf_math.cuh"
 #include "xf_launch.h"
+#include "xf_tma.cuh"
 
 #ifndef XF_NS
 #error "XF_NS must be defined"
@@ -488,6 +489,20 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 	}
 }
 
+// the same without rho (the marching sweeps take rho from the staged copy of U)
+template <class C>
+__device__ __forceinline__ void side_scalars(const XfDev &d, long long id, XfSide<C> &s)
+{
+	s.u = d.u[id], s.v = d.v[id], s.w = d.w[id], s.H = d.H[id], s.p = d.p[id];
+	if constexpr (C::COP)
+	{
+		s.g3 = d.g3[id], s.dpdrho = d.dpdrho[id], s.e = d.e[id], s.prho = d.prho[id];
+#pragma unroll
+		for (int n = 0; n < C::NC; n++)
+			s.y[n] = d.y[n * d.N + id], s.dpdrhoi[n] = d.dpdrhoi[n * d.N + id];
+	}
+}
+
 #ifndef XF_MINB_X
 #define XF_MINB_X 4   // resident blocks per SM the x sweep is compiled for (register cap 65536 / (XF_MINB_X * 128))
 #endif
@@ -497,8 +512,8 @@ __device__ __forceinline__ void load_side(const XfDev &d, const double *__restri
 #ifndef XF_TX_
 #define XF_TX_ 128
 #endif
-#ifndef XF_TF_
-#define XF_TF_ 8
+#ifndef XF_SWEEP_TMA
+#define XF_SWEEP_TMA 1 // y / z sweeps: the conserved-variable pencil of a tile is one TMA bulk-tensor copy straight into its shared-memory slot (0: per-thread loads)
 #endif
 #ifndef XF_SIDE_EARLY
 #define XF_SIDE_EARLY 0 // 1: issue the face-side loads before the stencil staging (their latency overlaps the staging)
@@ -516,36 +531,41 @@ struct XfTx
 	static constexpr int V = (WENO != 6) ? XF_TX_ : XF_TX_BIG;
 	static constexpr int MINB = (WENO != 6) ? XF_MINB_X : (512 / XF_TX_BIG);
 };
-#ifndef XF_TW_
-#define XF_TW_ 32
-#endif
 constexpr int XF_TW = XF_TW_; // y/z sweeps: tile width in x
 constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 
-template <class C, int DIR, int WENO, bool PP>
-__global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, DIR == 0 ? XfTx<WENO, PP>::MINB : XF_MINB_YZ) k_sweep(XfDev d, const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */)
+// ACC (x sweep of the marching path only): instead of storing the wall flux, write LU = 0.0 + (F_{i-1} - F_i) * _dx -- a compile-time
+// switch: as a run-time branch the extra tail cost the plain x sweep 6.7 % (75.6 vs 70.8 ms per step at 512^3; four 128-thread blocks
+// per SM at four places of a long instruction stream are sensitive to its length)
+template <class C, int DIR, int WENO, bool PP, bool ACC = false>
+__global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, DIR == 0 ? XfTx<WENO, PP>::MINB : XF_MINB_YZ) k_sweep(XfDev d, const __grid_constant__ CUtensorMap tmU /* y / z sweeps: the sweep input as a 4-D tensor, box = one tile's stencil rows */,
+		const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */,
+		double *__restrict__ LU /* ACC */)
 {
+	constexpr int mode = ACC ? XF_MODE_ACC : XF_MODE_FW;
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P, XF_TX = XfTx<WENO, PP>::V;
-	extern __shared__ double smem[];
+	extern __shared__ __align__(128) double smem[];
 	XfSide<C> sl, sr;
 	XfRoe<C> R;
 	SmemStencil<C, WENO> st;
 	long long id_l;
 	bool valid;
-	int sweep_tile = 0;
+	int sweep_tile = 0, ipos = 0;
 
 	if constexpr (DIR == 0)
 	{
 		constexpr int ncell = XF_TX + NST - 1;
 		double *sU = smem, *sF = smem + E * ncell, *sL = smem + 2 * E * ncell;
 		// grid: x = XF_TX-cell chunks of the linear index space of one z-plane, y = inner plane (32-bit index arithmetic;
-		// stencils of valid faces never leave their row, so cells outside the plane only feed idle threads)
+		// stencils of valid faces never leave their row, so cells outside the plane only feed idle threads).  ACC mode: a cell's
+		// divergence needs the face on its left too, so consecutive chunks overlap by one face (thread 0 only seeds)
 		const int kpl = kp0 + blockIdx.y;
-		const int q0 = blockIdx.x * XF_TX;
+		const int q0 = (mode == XF_MODE_FW) ? blockIdx.x * XF_TX : blockIdx.x * (XF_TX - 1) - 1;
 		const long long id0 = (long long)kpl * d.sZ + q0;
 		id_l = id0 + threadIdx.x;
 		const unsigned ql = unsigned(q0) + threadIdx.x;
 		const int j = int(ql / unsigned(d.Xp)), i = int(ql - unsigned(j) * unsigned(d.Xp));
+		ipos = i;
 		valid = ql < unsigned(d.sZ) && i >= d.Bx - 1 && i < d.Bx + d.Xi && j >= d.By && j < d.By + d.Yi;
 		if (XF_SIDE_EARLY && valid)
 			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + 1, sr);
@@ -588,12 +608,60 @@ __global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, 
 		id_l = DIR == 1 ? ((long long)k * d.Ymax + qf) * d.Xp + i : ((long long)qf * d.Ymax + j) * d.Xp + i;
 		if (XF_SIDE_EARLY && valid)
 			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + sS, sr);
-		for (int r = ty; r < nrow; r += XF_TF)
+		if constexpr (XF_SWEEP_TMA != 0)
+		{ // the conserved variables of the whole tile (nrow rows x XF_TW cells x E components) arrive by ONE cp.async.bulk.tensor in
+		  // their final place (the staged pencil of U is a plain copy; rows / columns outside the arrays are zero-filled by the
+		  // hardware); meanwhile every thread loads the primitives of its (at most two) cells, then forms 0.5 F and the wave speeds
+			unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + (2 * E + 3) * ncell);
+			if (threadIdx.x == 0)
+			{
+				xf_mbar_init(bar, 1);
+				xf_mbar_expect_tx(bar, unsigned(E * ncell * sizeof(double)));
+				xf_tma_load_4d(sU, &tmU, d.Bx + bx * XF_TW, DIR == 1 ? f0 - P : j, DIR == 1 ? k : f0 - P, 0, bar);
+			}
+			constexpr int NR = (nrow + XF_TF - 1) / XF_TF, NC = C::NC;
+			double pu[NR], pv[NR], pw[NR], pp_[NR], pc[NR], py[NR][NC > 0 ? NC : 1];
+#pragma unroll
+			for (int it = 0; it < NR; it++)
+			{
+				const int r = ty + it * XF_TF, q = f0 - P + r;
+				const bool ok = r < nrow && iok && q >= 0 && q < nmax;
+				const long long id = ok ? (DIR == 1 ? ((long long)k * d.Ymax + q) * d.Xp + i : ((long long)q * d.Ymax + j) * d.Xp + i) : 0;
+				pu[it] = ok ? d.u[id] : 0.0, pv[it] = ok ? d.v[id] : 0.0, pw[it] = ok ? d.w[id] : 0.0, pp_[it] = ok ? d.p[id] : 0.0, pc[it] = ok ? d.c[id] : 0.0;
+#pragma unroll
+				for (int s = 0; s < NC; s++)
+					py[it][s] = ok ? d.y[s * d.N + id] : 0.0;
+			}
+			__syncthreads(); // the initialised barrier is visible to every thread
+			xf_mbar_wait(bar, 0);
+#pragma unroll
+			for (int it = 0; it < NR; it++)
+			{
+				const int r = ty + it * XF_TF, c = r * XF_TW + tx;
+				if (r < nrow)
+				{
+					const double un = DIR == 1 ? pv[it] : pw[it], m = sU[(1 + DIR) * ncell + c];
+					sF[0 * ncell + c] = 0.5 * m;
+					sF[1 * ncell + c] = 0.5 * (m * pu[it]);
+					sF[2 * ncell + c] = 0.5 * (DIR == 1 ? m * pv[it] + pp_[it] : m * pv[it]);
+					sF[3 * ncell + c] = 0.5 * (DIR == 2 ? m * pw[it] + pp_[it] : m * pw[it]);
+					sF[4 * ncell + c] = 0.5 * ((sU[4 * ncell + c] + pp_[it]) * un);
+#pragma unroll
+					for (int s = 0; s < NC; s++)
+						sF[(5 + s) * ncell + c] = 0.5 * (m * py[it][s]);
+					sL[c] = fabs(un - pc[it]), sL[ncell + c] = fabs(un), sL[2 * ncell + c] = fabs(un + pc[it]);
+				}
+			}
+		}
+		else
 		{
-			const int q = f0 - P + r; // index along the sweep of this staged row
-			const bool ok = iok && q >= 0 && q < nmax;
-			const long long id = DIR == 1 ? ((long long)k * d.Ymax + q) * d.Xp + i : ((long long)q * d.Ymax + j) * d.Xp + i;
-			stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, r * XF_TW + tx);
+			for (int r = ty; r < nrow; r += XF_TF)
+			{
+				const int q = f0 - P + r; // index along the sweep of this staged row
+				const bool ok = iok && q >= 0 && q < nmax;
+				const long long id = DIR == 1 ? ((long long)k * d.Ymax + q) * d.Xp + i : ((long long)q * d.Ymax + j) * d.Xp + i;
+				stage_cell<C, DIR>(d, U, ok ? id : 0, ok, sU, sF, sL, ncell, r * XF_TW + tx);
+			}
 		}
 		if (XF_SIDE_EARLY == 2 && valid)
 			xf_roe_state<C>(sl, sr, d.gamma0, R);
@@ -602,27 +670,54 @@ __global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, 
 		if (!XF_SIDE_EARLY && valid)
 			load_side<C>(d, U, id_l, sl), load_side<C>(d, U, id_l + sS, sr);
 	}
-	if (!valid)
+	if (!valid && !(DIR == 0 && mode != XF_MODE_FW))
 		return;
-	if (XF_SIDE_EARLY != 2)
-		xf_roe_state<C>(sl, sr, d.gamma0, R);
-	double glf[3] = {d.red[XF_RED_GLF + DIR * 3 + 0], d.red[XF_RED_GLF + DIR * 3 + 1], d.red[XF_RED_GLF + DIR * 3 + 2]};
 	double F[E];
-	xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, DIR == 0 ? d.dx : (DIR == 1 ? d.dy : d.dz), F);
-	if constexpr (PP)
-	{ // (a template parameter: as a run-time branch the limiter cost the unlimited sweeps 2-4 %)  PositivityPreservingKernel runs over the inner cells (ConVenction_block.hpp:330-410): the face below the first inner
-	  // cell (the first face of every pencil) is never limited
-		bool lim;
-		if constexpr (DIR == 0)
-			lim = int((unsigned(blockIdx.x) * XF_TX + threadIdx.x) % unsigned(d.Xp)) >= d.Bx;
-		else
-			lim = (sweep_tile * XF_TF + threadIdx.x / XF_TW) > 0;
-		if (lim)
-			xf_positivity<C, WENO>(st, d.red[XF_RED_PPL + DIR], d.CFL, F);
+	if (valid)
+	{
+		if (XF_SIDE_EARLY != 2)
+			xf_roe_state<C>(sl, sr, d.gamma0, R);
+		double glf[3] = {d.red[XF_RED_GLF + DIR * 3 + 0], d.red[XF_RED_GLF + DIR * 3 + 1], d.red[XF_RED_GLF + DIR * 3 + 2]};
+		xf_face_flux<C, DIR, WENO>(st, R, d.alpha, glf, DIR == 0 ? d.dx : (DIR == 1 ? d.dy : d.dz), F);
+		if constexpr (PP)
+		{ // (a template parameter: as a run-time branch the limiter cost the unlimited sweeps 2-4 %)  PositivityPreservingKernel runs over the inner cells (ConVenction_block.hpp:330-410): the face below the first inner
+		  // cell (the first face of every pencil) is never limited
+			bool lim;
+			if constexpr (DIR == 0)
+				lim = ipos >= d.Bx;
+			else
+				lim = (sweep_tile * XF_TF + threadIdx.x / XF_TW) > 0;
+			if (lim)
+				xf_positivity<C, WENO>(st, d.red[XF_RED_PPL + DIR], d.CFL, F);
+		}
 	}
+	if constexpr (DIR == 0 && ACC)
+	{
+		{ // UpdateFluidLU, x part (Reconstruction_kernels.hpp:219-221): the left face's flux comes from the neighbouring thread through the
+		  // (now idle) stencil buffer; LU0 = 0.0; LU0 += (F_{i-1} - F_i) * _dx
+			__syncthreads();
+			double *ex = smem;
+			if (valid)
+			{
 #pragma unroll
-	for (int n = 0; n < E; n++)
-		Fw[n * d.N + id_l] = F[n];
+				for (int n = 0; n < E; n++)
+					ex[n * XF_TX + threadIdx.x] = F[n];
+			}
+			__syncthreads();
+			if (valid && threadIdx.x >= 1 && ipos >= d.Bx)
+			{
+#pragma unroll
+				for (int n = 0; n < E; n++)
+					LU[n * d.N + id_l] = 0.0 + (ex[n * XF_TX + threadIdx.x - 1] - F[n]) * d._dx;
+			}
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			Fw[n * d.N + id_l] = F[n];
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -758,6 +853,8 @@ __global__ void __launch_bounds__(256) k_nan(XfDev d, const double *__restrict__
 	if (bad)
 		d.err[2] = 1;
 }
+
+#include "xf_march.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // k_bc: FluidBCKernel{X,Y,Z} (BCs_kernels.hpp:9-258) launched as in BCs_block.cpp:81-213: one thread per ghost
@@ -952,85 +1049,136 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 	++*launches;
 	if constexpr (C::COP)
 	{
-		static int nsm = 0;
-		if (!nsm)
-		{
-			int dev = 0;
-			cudaGetDevice(&dev);
-			cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-		}
-		k_prim_hard<C><<<nsm * 8, 128, 0, s>>>(d, th, U, flags);
+		k_prim_hard<C><<<d.nsm * 8, 128, 0, s>>>(d, th, U, flags);
 		XF_CHECK_LAUNCH();
 		++*launches;
 	}
 	return 0;
 }
 
+// (the opt-in to > 48 KB of dynamic shared memory is per device and per kernel: set on every launch -- microseconds, no stream
+// operation, legal during graph capture -- rather than behind a per-process flag that would only cover the first device used)
 template <class C, int DIR, int WENO, bool PP>
-static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1)
+static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr)
 {
+	static const CUtensorMap no_map{};
 	if (kp1 <= kp0)
 		return 0;
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST;
-	static bool attr_done = false;
 	if constexpr (DIR == 0)
 	{
 		constexpr int XF_TX = XfTx<WENO, PP>::V;
 		constexpr size_t smem = size_t(2 * E + 3) * (XF_TX + NST - 1) * sizeof(double);
-		if (!attr_done)
-			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
-		const dim3 g((unsigned)((d.sZ + XF_TX - 1) / XF_TX), (unsigned)(kp1 - kp0));
-		k_sweep<C, DIR, WENO, PP><<<g, XF_TX, smem, s>>>(d, U, d.Fw[0], kp0);
+		cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const int cells = (mode == XF_MODE_FW) ? XF_TX : XF_TX - 1; // ACC: chunks overlap by one face
+		const dim3 g((unsigned)((d.sZ + cells - 1) / cells), (unsigned)(kp1 - kp0));
+		if (mode == XF_MODE_FW)
+			k_sweep<C, DIR, WENO, PP, false><<<g, XF_TX, smem, s>>>(d, no_map, U, d.Fw[0], kp0, LU);
+		else
+		{
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			k_sweep<C, DIR, WENO, PP, true><<<g, XF_TX, smem, s>>>(d, no_map, U, d.Fw[0], kp0, LU);
+		}
 	}
 	else
 	{
-		constexpr size_t smem = size_t(2 * E + 3) * (XF_TF + NST - 1) * XF_TW * sizeof(double);
-		if (!attr_done)
-			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), attr_done = true;
+		constexpr size_t smem = size_t(2 * E + 3) * (XF_TF + NST - 1) * XF_TW * sizeof(double) + 16; // + the TMA mbarrier
+		if (XF_SWEEP_TMA && !tm)
+			return -1;
+		cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		dim3 g;
 		if (DIR == 1)
 			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = kp1 - kp0;
 		else
 			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = kp1 - kp0, g.z = d.Yi; // kp0, kp1: tile range of the z sweep
-		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, U, d.Fw[DIR], kp0);
+		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, tm ? *tm : no_map, U, d.Fw[DIR], kp0, nullptr);
 		(void)kp1;
 	}
 	XF_CHECK_LAUNCH();
 	return 0;
 }
 template <class C, int DIR, int WENO>
-static int sweep_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1)
+static int sweep_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr)
 {
-	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s, kp0, kp1) : sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1);
+#ifdef XF_ONLY_SBI
+	if (d.positivity || WENO != 5)
+		return -1;
+	if constexpr (WENO == 5)
+		return sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm);
+#else
+	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s, kp0, kp1, mode, LU, tm) : sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm);
+#endif
+}
+// x sweep of the fused path: z-planes [a.t0, a.t1), a.mode = XF_MODE_ACC (LU = 0.0 + d/dx part) or XF_MODE_FW
+template <class C>
+static int sweep_x_t(const XfDev &d, const double *U, const XfMarchArgs &a, cudaStream_t s)
+{
+	if (d.weno == 7)
+		return sweep_t<C, 0, 7>(d, U, s, a.t0, a.t1, a.mode, a.LU);
+	if (d.weno == 6)
+		return sweep_t<C, 0, 6>(d, U, s, a.t0, a.t1, a.mode, a.LU);
+	return sweep_t<C, 0, 5>(d, U, s, a.t0, a.t1, a.mode, a.LU);
+}
+// marching y / z sweep (xf_march.cuh)
+template <class C, int DIR, int WENO, bool PP>
+static int march_pp_t(const XfDev &d, const XfTma &tm, const double *UI, const XfMarchArgs &a, cudaStream_t s)
+{
+	using G = XfMarchGeom<C, WENO>;
+	if (a.t1 <= a.t0 || a.cb <= a.ca)
+		return 0;
+	cudaFuncSetAttribute(k_march<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+	const dim3 g((unsigned)((d.Xi + G::W - 1) / G::W), (unsigned)(a.t1 - a.t0), (unsigned)a.nseg);
+	k_march<C, DIR, WENO, PP><<<g, G::NT, G::smem_bytes, s>>>(d, tm.U, tm.P, tm.Y, UI, a);
+	XF_CHECK_LAUNCH();
+	return 0;
+}
+template <class C, int DIR>
+static int march_t(const XfDev &d, const XfTma &tm, const double *UI, const XfMarchArgs &a, cudaStream_t s)
+{
+#ifdef XF_ONLY_SBI
+	if (d.weno != 5 || d.positivity)
+		return -1;
+	return march_pp_t<C, DIR, 5, false>(d, tm, UI, a, s);
+#endif
+	if (d.weno == 7)
+		return d.positivity ? march_pp_t<C, DIR, 7, true>(d, tm, UI, a, s) : march_pp_t<C, DIR, 7, false>(d, tm, UI, a, s);
+	if (d.weno == 6)
+		return d.positivity ? march_pp_t<C, DIR, 6, true>(d, tm, UI, a, s) : march_pp_t<C, DIR, 6, false>(d, tm, UI, a, s);
+	return d.positivity ? march_pp_t<C, DIR, 5, true>(d, tm, UI, a, s) : march_pp_t<C, DIR, 5, false>(d, tm, UI, a, s);
 }
 // kp0, kp1: z-plane range [kp0, kp1) of the x and y sweeps (absolute plane indices inside [Bz, Bz + Zi)); the z sweep always
 // covers the block
 template <class C>
-static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1)
+static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, const CUtensorMap *tmy, const CUtensorMap *tmz)
 {
 	int rc = 0;
 	const bool dx = d.DimX && (dirmask & 1), dy = d.DimY && (dirmask & 2), dz = d.DimZ && (dirmask & 4);
 	if (d.weno == 7)
 	{
 		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s, kp0, kp1), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s, tz0, tz1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
 	}
 	else if (d.weno == 6)
 	{
 		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s, kp0, kp1), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s, tz0, tz1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
 	}
 	else
 	{
 		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s, kp0, kp1), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s, tz0, tz1), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
 	}
 	return rc;
 }
 
+#ifdef XF_ONLY_SBI // tuning builds: only the Emax = 9 configuration is instantiated (seconds instead of minutes per variant)
+#define XF_DISPATCH_CFG(ns, cop, ...)                          \
+	if ((cop) && (ns) == 5) { using C = XfCfg<5, true>; __VA_ARGS__; } \
+	else return -1;
+#else
 #define XF_DISPATCH_CFG(ns, cop, ...)                          \
 	if (!(cop)) { using C = XfCfg<1, false>; __VA_ARGS__; }    \
 	else if ((ns) == 2) { using C = XfCfg<2, true>; __VA_ARGS__; } \
@@ -1038,6 +1186,7 @@ static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *
 	else if ((ns) == 4) { using C = XfCfg<4, true>; __VA_ARGS__; } \
 	else if ((ns) == 5) { using C = XfCfg<5, true>; __VA_ARGS__; } \
 	else return -1;
+#endif
 
 #define XF_DISPATCH_E(E_, ...)                          \
 	switch (E_)                                         \
@@ -1057,15 +1206,28 @@ int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, 
 // kp0, kp1: z-plane range of the x / y sweeps (< 0: all inner planes); tz0, tz1: tile range of the z sweep (tile t = faces
 // Bz - 1 + XF_TF t ... ; < 0: all xf_z_tiles() of them)
 int xf_z_tiles(const XfDev &d) { return (d.Zi + 1 + XF_TF - 1) / XF_TF; }
-int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1)
+int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1,
+				  const CUtensorMap *tmy, const CUtensorMap *tmz)
 {
 	if (kp0 < 0)
 		kp0 = d.Bz, kp1 = d.Bz + d.Zi;
 	if (tz0 < 0)
 		tz0 = 0, tz1 = xf_z_tiles(d);
-	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1));
+	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz));
 }
 int z_tile_faces() { return XF_TF; }
+int launch_sweep_x(const XfDev &d, int ns, int cop, const double *U, const XfMarchArgs &a, cudaStream_t s)
+{
+	XF_DISPATCH_CFG(ns, cop, return sweep_x_t<C>(d, U, a, s));
+}
+int launch_march(const XfDev &d, int ns, int cop, const XfTma &tm, const double *UI, const XfMarchArgs &a, int dir, cudaStream_t s)
+{
+	if (dir == 1)
+	{
+		XF_DISPATCH_CFG(ns, cop, return march_t<C, 1>(d, tm, UI, a, s));
+	}
+	XF_DISPATCH_CFG(ns, cop, return march_t<C, 2>(d, tm, UI, a, s));
+}
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 int launch_lu(const XfDev &d, int E_, double *LU, cudaStream_t s)
 {

@@ -1,14 +1,25 @@
 // xf_launch.h -- host-callable launchers exported by each compiled flavour of xf_kernels.cu
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "xf_types.h"
+
+// TMA tensor maps of one sweep input for one direction: conserved variables [E][N], (u v w p c) [5][N], Y [NC][N], each a 4-D
+// tensor (x, y, z, component) with a box of XF_MW x TF cells along the sweep
+struct XfTma
+{
+	CUtensorMap U, P, Y;
+};
 
 #define XF_DECLARE_LAUNCHERS(NS)                                                                                              \
 	namespace NS                                                                                                              \
 	{                                                                                                                         \
 		int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1); \
-		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1); \
+		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, \
+						  const CUtensorMap *tmy, const CUtensorMap *tmz);                                                      \
 		int xf_z_tiles(const XfDev &d);                                                                                       \
+		int launch_sweep_x(const XfDev &d, int ns, int cop, const double *U, const XfMarchArgs &a, cudaStream_t s);           \
+		int launch_march(const XfDev &d, int ns, int cop, const XfTma &tm, const double *UI, const XfMarchArgs &a, int dir, cudaStream_t s); \
 		int z_tile_faces();                                                                                                   \
 		int launch_lu(const XfDev &d, int E, double *LU, cudaStream_t s);                                                     \
 		int launch_rk(const XfDev &d, int E, double *U, double *U1, const double *LU, double dt, const double *dt_dev,       \

@@ -13,6 +13,38 @@
 #define XF_RED_PPL 16        // [16..18] uvw_c_max of the last GetDt, kept for the positivity-preserving limiter
 #define XF_RED_COUNT 20
 
+// tiled y / z sweeps (k_sweep): tile = XF_TW_ cells in x by XF_TF_ faces along the sweep; the TMA box of a tile's conserved pencil has
+// XF_TF_ + NST - 1 rows (NST = 6 stencil cells for WENO5 / CU6, 8 for WENO7)
+#ifndef XF_TW_
+#define XF_TW_ 32
+#endif
+#ifndef XF_TF_
+#define XF_TF_ 8
+#endif
+#define XF_TILE_ROWS(weno) (XF_TF_ + ((weno) == 7 ? 8 : 6) - 1)
+
+// marching y / z sweeps (k_march, xf_march.cuh): tile = XF_MW cells in x by TF faces along the sweep per iteration
+#ifndef XF_MW
+#define XF_MW 16
+#endif
+#ifndef XF_MTF_
+#define XF_MTF_ 16
+#endif
+#define XF_MTF(weno) ((weno) == 7 && XF_MTF_ == 16 ? 15 : XF_MTF_)   // WENO7's 8-cell stencil needs two more ring rows: 15 faces keep two blocks per SM at Emax = 9
+#ifndef XF_MARCH_MINB
+#define XF_MARCH_MINB 2     // resident blocks per SM k_march is compiled for
+#endif
+#ifndef XF_MARCH_ALIAS
+#define XF_MARCH_ALIAS 0    // 1: the flux-exchange rows live in the (consumed) landing buffer: 2 more barriers per iteration, 19 KB less shared memory per block
+#endif
+#ifndef XF_MARCH_SIDEPF
+#define XF_MARCH_SIDEPF 1   // 1: the face-side scalars of the next iteration are loaded before the closing barrier of this one
+#endif
+// what a sweep does with the wall flux it has formed
+#define XF_MODE_FW 0    // store it (block-level API: FluxFw / FluxGw / FluxHw of the reference)
+#define XF_MODE_ACC 1   // LU (+)= (F_{f-1} - F_f) * _dl   (UpdateFluidLU, one direction at a time in the reference's x -> y -> z order)
+#define XF_MODE_RK 2    // the same for the last direction, then NaN guard + SSP-RK3 stage update; LU never leaves the registers
+
 struct XfDev
 {
 	int Xmax, Ymax, Zmax, Xp;          // Xp: padded x pitch
@@ -20,19 +52,34 @@ struct XfDev
 	int DimX, DimY, DimZ;
 	int weno, alpha, ghost;            // scheme + GhostSpecies
 	int positivity;                    // equations.PositivityPreserving (read_json.cpp:68)
+	int nsm;                           // SM count of the context's device
 	long long N;                       // field stride = Xp*Ymax*Zmax (doubles between components)
 	long long sY, sZ;                  // cell strides along y and z
 	double _dx, _dy, _dz, CFL, gamma0;
 	double dx, dy, dz;                 // mesh widths (WENO-CU6 epsilon = 1e-8 dl dl)
 	// scalar work arrays [N] (reference FlowData, global_setup.h:218-250) + per-cell pieces of the
 	// Roe-averaged pressure derivatives (Utils_device.hpp:14-35), which are pure functions of one cell
-	double *u, *v, *w, *p, *H, *c, *T, *g3, *dpdrho, *e, *prho;
+	double *u, *v, *w, *p, *H, *c, *T, *g3, *dpdrho, *e, *prho; // u, v, w, p, c are ONE allocation [5][N] in that order (one TMA tensor map)
 	double *y;                         // [NS][N]
 	double *dpdrhoi;                   // [NC][N]
-	double *Fw[3];                     // wall fluxes [E][N] per direction
+	double *Fw[3];                     // wall fluxes [E][N] per direction (allocated by the first xf_get_lu; the fused path never stores them)
 	double *red;                       // XF_RED_* slots
 	int *err;                          // [4]
 	unsigned *hard_ids, *hard_count;   // cells whose Newton iteration needs more than XF_NEWTON_FAST steps (k_prim -> k_prim_hard)
+};
+
+// arguments of one sweep launch beyond the block description (k_sweep x direction, k_march y / z)
+struct XfMarchArgs
+{
+	int mode;             // XF_MODE_FW / ACC / RK
+	int first;            // this direction is the first active one: LU starts from 0.0
+	int flag, guard;      // RK stage 1..3; NaN guard on
+	int t0, t1;           // transverse range (x, y sweeps: z-planes [t0, t1); z sweep: rows j, always [By, By + Yi))
+	int ca, cb;           // y / z: cells [ca, cb) along the sweep to form the divergence for (absolute indices); faces ca - 1 .. cb - 1 are computed
+	int nseg, seglen;     // y / z: the march is cut in nseg segments (gridDim.z) of seglen cells
+	double *U, *U1, *LU;  // RK: fields of the update; ACC: LU
+	double *Fw;           // FW: this direction's wall-flux field
+	const double *dt_dev;
 };
 
 // NASA-9 tables, re-laid-out per temperature range so that a warp-uniform branch on the range gives

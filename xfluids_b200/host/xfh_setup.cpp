@@ -161,6 +161,10 @@ namespace xfh
 		if (!match("-fp").empty()) fp_mode = std::atoi(match("-fp")[0].c_str());
 		if (!match("-pp").empty()) PositivityPreserving = std::atoi(match("-pp")[0].c_str()) != 0;
 		if (!match("-cfl").empty()) bl.CFLnumber = std::atof(match("-cfl")[0].c_str());
+		std::vector<int> bcv = ints("-bc"); // run-time override of mesh.Boundarys (xmin, xmax, ymin, ymax, zmin, zmax; BConditions codes)
+		if (bcv.size() == 6)
+			for (int i = 0; i < 6; i++)
+				Boundarys[i] = bcv[i];
 		if (!match("-alpha").empty())
 		{
 			const std::string a = match("-alpha")[0];
