@@ -97,3 +97,42 @@ def test_host_step_overlapped_upload_is_bitwise_identical(case, res, weno, pp, c
     assert outs[0][1] == outs[1][1]
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.parametrize("js,grid,E,scaling,extra", [("expanded-jet.json", (32, 16, 32), 7, "strong", []), ("shock-bubble.json", (32, 16, 16), 9, "weak", ["-weno=6", "-pp=1", "-cfl=0.9"]),
+                                                      ("shock-bubble.json", (24, 12, 24), 9, "strong", ["-alpha=GLF", "-blocks"])])
+def test_executable_two_ranks_equal_one_block_bitwise(tmp_path, js, grid, E, scaling, extra):
+    """`xfluids ... -mpi=1,1,2`: one process, one host thread per GPU, the C++ NCCL slab stepper (halo exchange overlapped with interior
+    work, dt MAX-reduced on the device) -- the reference's N > 1 flow (mpiPacks.cpp:357-505, Fluids.cpp:902-913) entirely in C++.
+    The two ranks' checkpoints must tile the single-GPU run's checkpoint BIT FOR BIT (-blocks: the call-by-call loop with the
+    host-side reductions; GLF: the nine running maxima are MAX-reduced every stage)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from xfluids_b200 import host
+    settings = os.path.join(xfref.REPO, "settings", js)
+    nx, ny, nz = grid
+    one, two = str(tmp_path / "one.ckpt"), str(tmp_path / "two.ckpt")
+    if scaling == "strong":
+        run([settings, "-run=%d,%d,%d,6" % grid, "-ckpt=" + one, "-quiet"] + extra)
+        out = run([settings, "-run=%d,%d,%d,6" % grid, "-mpi=1,1,2", "-mpi-s=strong", "-ckpt=" + two, "-quiet"] + extra)
+        zi = nz // 2
+        s1 = host.Setup(settings, ["-run=%d,%d,%d" % grid] + extra)
+    else:
+        s0 = host.Setup(settings, ["-run=%d,%d,%d" % grid] + extra)
+        dom = "-domain=%.17g,%.17g,%.17g" % (0.1, 0.05, 0.05 * 2)      # shock-bubble.json DOMAIN_Size with the z extent doubled
+        run([settings, "-run=%d,%d,%d,6" % (nx, ny, 2 * nz), dom, "-ckpt=" + one, "-quiet"] + extra)
+        out = run([settings, "-run=%d,%d,%d,6" % grid, "-mpi=1,1,2", "-mpi-s=weak", "-ckpt=" + two, "-quiet"] + extra)
+        zi = nz
+        s1 = host.Setup(settings, ["-run=%d,%d,%d" % (nx, ny, 2 * nz), dom] + extra)
+        del s0
+    assert "ranks=2" in out and "steps=6" in out
+    b = s1.block
+    plane = b.Xmax * b.Ymax * E
+    st1, t1, U1 = read_ckpt(one, b.Zmax * plane)
+    U1 = U1.reshape(b.Zmax, plane)
+    Bz = b.Bwidth_Z
+    for r in range(2):
+        st, t, U = read_ckpt(two + ".rank%d" % r, (zi + 2 * Bz) * plane)
+        assert (st, t) == (st1, t1)
+        assert np.array_equal(U.reshape(zi + 2 * Bz, plane)[Bz:Bz + zi], U1[Bz + r * zi:Bz + (r + 1) * zi]), "rank %d" % r

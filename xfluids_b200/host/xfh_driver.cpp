@@ -86,14 +86,49 @@ namespace xfh
 	{
 		fluids.emplace_back(new Fluid(setup, device));
 	}
+	XFLUIDS::~XFLUIDS()
+	{
+		if (slab)
+			xf_slab_destroy(slab);
+	}
+	void XFLUIDS::AttachSlab(xf_comm *comm)
+	{
+		Fluid &f = *fluids[0];
+		if (xf_slab_create(f.ctx, comm, f.BCs, Ss.artificial, Ss.weno, nullptr, &slab) != XF_OK)
+			throw std::runtime_error(std::string("xf_slab_create failed: ") + xf_slab_last_error());
+		comm_ = comm;
+		xf_slab *sl = slab;
+		f.halo_exchange = [sl](double *UI)
+		{ return xf_slab_halo(sl, UI); };
+		f.allreduce_max3 = [sl](double *m3)
+		{ return xf_slab_allreduce_max_host(sl, m3, 3); };
+	}
+	// the guards of one rank decide for all (the reference all-reduces its error counters the same way, XFLUIDS.cpp:567-595)
+	static bool any_rank(xf_slab *slab, bool err)
+	{
+		if (!slab)
+			return err;
+		double v = err ? 1.0 : 0.0;
+		if (xf_slab_allreduce_max_host(slab, &v, 1) != XF_OK)
+			throw std::runtime_error(std::string("error all-reduce failed: ") + xf_slab_last_error());
+		return v != 0.0;
+	}
 	void XFLUIDS::AllocateMemory() { fluids[0]->AllocateFluidMemory(); }
 	void XFLUIDS::InitialCondition() { fluids[0]->InitialU(); }
 	void XFLUIDS::BoundaryCondition(int flag) { fluids[0]->BoundaryCondition(flag); }
-	bool XFLUIDS::UpdateStates(int flag) { return fluids[0]->UpdateFluidStates(flag); }
+	bool XFLUIDS::UpdateStates(int flag)
+	{
+		const bool err = any_rank(slab, fluids[0]->UpdateFluidStates(flag));
+		// global Lax-Friedrichs on several ranks: the running maxima of |lambda| are MAX-reduced before any sweep reads them (the
+		// reference's MPI build reduces eigen_block the same way, ConVenction_block.hpp:115-215)
+		if (slab && Ss.artificial == 3 && Ss.weno != 7 && xf_comm_allreduce_max(comm_, xf_device_glfmax(fluids[0]->ctx), 9, nullptr) != XF_OK)
+			throw std::runtime_error(std::string("GLF all-reduce failed: ") + xf_slab_last_error());
+		return err;
+	}
 	double XFLUIDS::ComputeTimeStep() { return fluids[0]->GetFluidDt(); }
 	void XFLUIDS::ComputeLU(int flag) { fluids[0]->ComputeFluidLU(flag); }
 	void XFLUIDS::UpdateU(int flag) { fluids[0]->UpdateFluidURK3(flag, dt); }
-	bool XFLUIDS::EstimateNAN(int flag) { return fluids[0]->EstimateFluidNAN(flag); }
+	bool XFLUIDS::EstimateNAN(int flag) { return any_rank(slab, fluids[0]->EstimateFluidNAN(flag)); }
 
 	bool XFLUIDS::RungeKuttaSP3rd(int flag)
 	{
@@ -124,15 +159,18 @@ namespace xfh
 		while (TimeLoop < Ss.OutTimeStamps.size())
 		{
 			const double target_t = (physicalTime < Ss.OutTimeStamps[TimeLoop].time) ? Ss.OutTimeStamps[TimeLoop].time : Ss.OutTimeStamps[TimeLoop++].time;
-			if (fused && !f.halo_exchange)
+			if (fused)
 			{
 				if (physicalTime < target_t && Iteration < Ss.nStepmax)
 				{
 					int done = 0, err = 0;
 					XFCK(xf_set_time(f.ctx, physicalTime));
-					int rc = xf_run(f.ctx, f.d_U, f.d_U1, f.d_LU, f.BCs, Ss.nStepmax - Iteration, target_t, &done, &physicalTime, &err);
+					// one GPU: CUDA-graph replay of whole steps; z-slabs: the slab stepper (halo exchange overlapped with interior work, dt
+					// MAX-reduced on the device) -- both keep dt and the physical time on the device
+					int rc = slab ? xf_slab_run(slab, f.d_U, f.d_U1, f.d_LU, Ss.nStepmax - Iteration, target_t, &done, &physicalTime, &err)
+								  : xf_run(f.ctx, f.d_U, f.d_U1, f.d_LU, f.BCs, Ss.nStepmax - Iteration, target_t, &done, &physicalTime, &err);
 					if (rc != XF_OK && rc != XF_ERR_NUMERIC)
-						throw std::runtime_error(std::string("xf_run failed: ") + xf_last_error());
+						throw std::runtime_error(std::string("fused time loop failed: ") + (slab ? xf_slab_last_error() : xf_last_error()));
 					Iteration += done;
 					XFCK(xf_get_time(f.ctx, nullptr, &dt));
 					error_out = err != 0;

@@ -48,6 +48,13 @@ namespace xfh
 		double loop_seconds = 0;
 
 		XFLUIDS(Setup &setup, int device);
+		~XFLUIDS();
+		// multi-GPU (z-slabs, one XFLUIDS per rank -- a thread of `xfluids -mpi=1,1,N` or a process): binds this rank's fluid to the
+		// C++ slab stepper of the CUDA library (xf_slab_*, NCCL over NVLink).  Sets Fluid::halo_exchange / allreduce_max3, the two
+		// places where the reference calls MPI (BCs_block.cpp:50-217, Fluids.cpp:902-913); Evolution(fused) then runs xf_slab_run.
+		void AttachSlab(xf_comm *comm);
+		xf_slab *slab = nullptr;
+		xf_comm *comm_ = nullptr;
 		void AllocateMemory();
 		void InitialCondition();
 		void BoundaryCondition(int flag = 0);
