@@ -331,6 +331,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries exactly ONE line, the JSON record: whatever native libraries print on fd 1 (NCCL's version banner at communicator
+    # creation) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if os.environ.get("WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
         # torchrun pins OMP_NUM_THREADS=1; the host-side initial condition (OpenMP) gets this rank's share of the cores
@@ -574,7 +579,8 @@ def main():
             line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if hptr:
         L.dll.xf_host_free_pinned(hptr)
         stepper.close()

@@ -26,6 +26,7 @@ static int fail(int code, const std::string &m)
 		if (e__ != cudaSuccess)                                                                         \
 			return fail(XF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
 	} while (0)
+#define XF_DEVICE(c) CU(cudaSetDevice((c)->device)) /* every entry point that launches or copies: several contexts / devices may live in one process */
 #define KL(call)                                                                                        \
 	do                                                                                                  \
 	{                                                                                                   \
@@ -299,6 +300,7 @@ extern "C"
 	}
 	int xf_synchronize(xf_ctx *c)
 	{
+		XF_DEVICE(c);
 		CU(cudaStreamSynchronize(c->stream));
 		return XF_OK;
 	}
@@ -320,6 +322,7 @@ extern "C"
 	}
 	int xf_field_free(xf_ctx *c, double *p)
 	{
+		XF_DEVICE(c);
 		CU(cudaStreamSynchronize(c->stream));
 		CU(cudaFree(p));
 		return XF_OK;
@@ -332,6 +335,7 @@ extern "C"
 	}
 	int xf_upload_aos(xf_ctx *c, double *d_field, const double *h_aos)
 	{
+		XF_DEVICE(c);
 		if (ensure_stage(c))
 			return XF_ERR_CUDA;
 		CU(cudaMemcpyAsync(c->stage, h_aos, c->ncells() * c->E * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -342,6 +346,7 @@ extern "C"
 	}
 	int xf_download_aos(xf_ctx *c, const double *d_field, double *h_aos)
 	{
+		XF_DEVICE(c);
 		if (ensure_stage(c))
 			return XF_ERR_CUDA;
 		KL(c->t->layout(c->d, c->E, const_cast<double *>(d_field), c->stage, 0, c->stream, 0, -1));
@@ -366,6 +371,7 @@ extern "C"
 	}
 	int xf_set_scalar(xf_ctx *c, const char *name, const double *h)
 	{
+		XF_DEVICE(c);
 		double *p = scalar_by_name(c, name);
 		if (!p)
 			return fail(XF_ERR_ARG, std::string("unknown scalar ") + name);
@@ -379,6 +385,7 @@ extern "C"
 	}
 	int xf_get_scalar(xf_ctx *c, const char *name, double *h)
 	{
+		XF_DEVICE(c);
 		double *p = scalar_by_name(c, name);
 		if (!p)
 			return fail(XF_ERR_ARG, std::string("unknown scalar ") + name);
@@ -400,12 +407,14 @@ extern "C"
 	// ---- block-level entry points ---------------------------------------------------------------
 	int xf_boundary(xf_ctx *c, double *U, const int bc[6])
 	{
+		XF_DEVICE(c);
 		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches, 7, -1, -1));
 		return XF_OK;
 	}
 	// planes [k0, k1) ; reset_dt: zero the dt maxima first (the first call of a gather)
 	static int update_states_range(xf_ctx *c, double *U, bool gather_dt, bool reset_dt, int k0, int k1)
 	{
+		XF_DEVICE(c);
 		int flags = 0;
 		if (gather_dt)
 		{
@@ -545,6 +554,7 @@ extern "C"
 	// to the NaN guard and the stage update in the same kernel, and neither wall fluxes nor LU reach HBM.
 	static int stage_sweeps(xf_ctx *c, double *U, double *U1, double *LU, int flag, int dirmask, int kp0, int kp1, int ka, int kb, bool finish)
 	{
+		XF_DEVICE(c);
 		const XfDev &d = c->d;
 		double *UI = flag == 1 ? U : U1;
 		const bool allz = ka < 0;
@@ -609,6 +619,7 @@ extern "C"
 	}
 	int xf_error_flags(xf_ctx *c, int flags[4])
 	{
+		XF_DEVICE(c);
 		CU(cudaMemcpyAsync(c->h_err, c->d.err, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 		for (int i = 0; i < 4; i++)
@@ -617,6 +628,7 @@ extern "C"
 	}
 	int xf_clear_errors(xf_ctx *c)
 	{
+		XF_DEVICE(c);
 		CU(cudaMemsetAsync(c->d.err, 0, 4 * sizeof(int), c->stream));
 		return XF_OK;
 	}
@@ -636,6 +648,7 @@ extern "C"
 	}
 	int xf_get_lu(xf_ctx *c, const double *U, double *LU)
 	{
+		XF_DEVICE(c);
 		// block-level form: the wall fluxes of the three directions are stored (the reference's FluxFw / Gw / Hw, readable through
 		// xf_get_wallflux_aos), then UpdateFluidLU forms the divergence
 		int rc;
@@ -683,6 +696,7 @@ extern "C"
 	}
 	int xf_estimate_nan(xf_ctx *c, const double *UI, const double *LU, int *error)
 	{
+		XF_DEVICE(c);
 		KL(c->t->nan(c->d, c->E, UI, LU, c->stream));
 		c->launches++;
 		if (error)
@@ -696,6 +710,7 @@ extern "C"
 	}
 	int xf_update_u_rk3(xf_ctx *c, double *U, double *U1, const double *LU, double dt, int flag)
 	{
+		XF_DEVICE(c);
 		if (flag < 1 || flag > 3)
 			return fail(XF_ERR_ARG, "flag must be 1..3");
 		KL(c->t->rk(c->d, c->E, U, U1, LU, dt, nullptr, flag, 0, 0, c->stream, -1, -1));
@@ -704,6 +719,7 @@ extern "C"
 	}
 	int xf_get_dt(xf_ctx *c, double *dt, double uvw_c_max[3])
 	{
+		XF_DEVICE(c);
 		// stand-alone reduction pass over the stored primitives, like the reference's GetDt; rho is component 0 of
 		// the field the primitives were last derived from (the reference keeps a separate rho array)
 		if (!c->lastUI)
@@ -726,6 +742,7 @@ extern "C"
 	// ---- fused path --------------------------------------------------------------------------------
 	int xf_dt_device(xf_ctx *c, double t_end)
 	{
+		XF_DEVICE(c);
 		KL(c->t->dt_final(c->d, t_end, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -784,7 +801,8 @@ extern "C"
 	}
 	int xf_get_time(xf_ctx *c, double *time, double *last_dt)
 	{
-		CU(cudaMemcpyAsync(c->h_pin, c->d.red + XF_RED_DT, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		XF_DEVICE(c);
+		CU(cudaMemcpyAsync(c->h_pin, c->d.red + XF_RED_DT, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 		if (last_dt)
 			*last_dt = c->h_pin[0];
@@ -792,8 +810,11 @@ extern "C"
 			*time = c->h_pin[1];
 		return XF_OK;
 	}
+	// time steps taken with dt > 0 since the context was created (device counter; call after xf_get_time, which fetched it)
+	static long long steps_taken(const xf_ctx *c) { return (long long)c->h_pin[2]; }
 	int xf_set_time(xf_ctx *c, double time)
 	{
+		XF_DEVICE(c);
 		c->h_pin[8] = time;
 		CU(cudaMemcpyAsync(c->d.red + XF_RED_TIME, c->h_pin + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
@@ -850,17 +871,18 @@ extern "C"
 			std::memcpy(c->gbc, bc, 6 * sizeof(int));
 		}
 		double t = 0, dt = 0;
-		int rc, done = 0, err = 0;
+		int rc, queued = 0, err = 0;
 		if ((rc = xf_get_time(c, &t, nullptr)))
 			return rc;
+		const long long steps0 = steps_taken(c);
 		int poll = 1; // steps between host checks of (time, error)
-		while (done < nsteps && t < t_end)
+		while (queued < nsteps && t < t_end)
 		{
-			int batch = poll < nsteps - done ? poll : nsteps - done;
+			int batch = poll < nsteps - queued ? poll : nsteps - queued;
 			for (int s = 0; s < batch; s++)
 				CU(cudaGraphLaunch(c->gexec, c->stream));
 			c->launches += c->glaunches * batch;
-			done += batch;
+			queued += batch;
 			int f[4];
 			if ((rc = xf_get_time(c, &t, &dt)) || (rc = xf_error_flags(c, f)))
 				return rc;
@@ -869,9 +891,14 @@ extern "C"
 				err = 1;
 				break;
 			}
-			// far from t_end: check less often (dt varies slowly); near it: every step, like the reference's loop
-			poll = (dt > 0 && (t_end - t) > 64.0 * dt) ? 16 : 1;
+			// far from t_end: check less often; near it: every step, like the reference's loop (XFLUIDS.cpp:172-199).  dt may GROW from
+			// step to step (start-up transients): never queue more steps than fit before t_end at four times the current dt, so that no
+			// replay runs with dt clipped to 0 (such a step would still renormalise species and re-round U -- ADVICE r1)
+			const double room = dt > 0 ? (t_end - t) / (4.0 * dt) : 1.0;
+			poll = room >= 16.0 ? 16 : (room >= 1.0 ? (int)room : 1);
 		}
+		// steps actually taken (dt > 0), counted on the device
+		const int done = (int)(steps_taken(c) - steps0);
 		if (steps_done)
 			*steps_done = done;
 		if (time_out)
@@ -1048,6 +1075,7 @@ extern "C"
 	}
 	int xf_halo_pack(xf_ctx *c, const double *U, int face, double *buf)
 	{
+		XF_DEVICE(c);
 		if (!c->d.DimZ || (face != 4 && face != 5))
 			return fail(XF_ERR_ARG, "halo faces are 4 (zmin) / 5 (zmax) of an active z dimension");
 		const int k0 = face == 4 ? c->d.Bz : c->d.Zmax - 2 * c->d.Bz;
@@ -1057,6 +1085,7 @@ extern "C"
 	}
 	int xf_halo_unpack(xf_ctx *c, double *U, int face, const double *buf)
 	{
+		XF_DEVICE(c);
 		if (!c->d.DimZ || (face != 4 && face != 5))
 			return fail(XF_ERR_ARG, "halo faces are 4 (zmin) / 5 (zmax) of an active z dimension");
 		const int k0 = face == 4 ? 0 : c->d.Zmax - c->d.Bz;

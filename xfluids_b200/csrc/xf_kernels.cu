@@ -416,6 +416,8 @@ __global__ void k_dt_final(XfDev d, double t_end)
 		dt = t_end - t;
 	r[XF_RED_DT] = dt;
 	r[XF_RED_TIME] = t + dt;
+	if (dt > 0.0)
+		r[XF_RED_STEPS] += 1.0;
 	// the positivity-preserving limiter of the coming stages reads uvw_c_max as this GetDt left it (ConVenction_block.hpp:332)
 	r[XF_RED_PPL + 0] = r[XF_RED_DTMAX + 0], r[XF_RED_PPL + 1] = r[XF_RED_DTMAX + 1], r[XF_RED_PPL + 2] = r[XF_RED_DTMAX + 2];
 	r[XF_RED_DTMAX + 0] = 0.0, r[XF_RED_DTMAX + 1] = 0.0, r[XF_RED_DTMAX + 2] = 0.0;

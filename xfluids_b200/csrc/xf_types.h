@@ -10,6 +10,7 @@
 #define XF_RED_GLF 3         // [3..11] running max |lambda|: dir*3 + {u-c, u, u+c}       (ConVenction_block.hpp:115-170)
 #define XF_RED_DT 12         // device-resident dt
 #define XF_RED_TIME 13       // device-resident physical time
+#define XF_RED_STEPS 14      // time steps taken with dt > 0 (k_dt_final): what xf_run reports, even if a replayed batch overshoots t_end
 #define XF_RED_PPL 16        // [16..18] uvw_c_max of the last GetDt, kept for the positivity-preserving limiter
 #define XF_RED_COUNT 20
 
