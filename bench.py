@@ -323,6 +323,8 @@ def main():
     ap.add_argument("--fp", type=int, default=0, help="0 strict (parity mode, default), 1 FMA contraction in the sweeps")
     ap.add_argument("--weno", type=int, default=5, help="5 WENO5-JS, 6 WENO-CU6, 7 WENO7-JS")
     ap.add_argument("--pp", type=int, default=0, help="1: positivity-preserving flux limiter on (fused into the sweep tails)")
+    ap.add_argument("--visc", type=int, default=0, help="1: viscous + heat-conduction + species-diffusion wall fluxes on (the shipped shock-bubble preset: --weno 6 --pp 1 --alpha GLF --visc 1)")
+    ap.add_argument("--alpha", default="LLF", choices=["ROE", "LLF", "GLF"], help="flux splitting (north_star: LLF)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-steps", type=int, default=2)
@@ -362,7 +364,7 @@ def main():
     w = WORKLOADS[args.workload]
     grid = tuple(int(x) for x in args.grid.split(",")) if args.grid else w["grid"]
     scaling = args.scaling or ("strong" if args.workload == "jet" else "weak")
-    cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=LLF", "-fp=%d" % args.fp, "-pp=%d" % args.pp]
+    cli = ["-run=%d,%d,%d" % grid, "-weno=%d" % args.weno, "-alpha=" + args.alpha, "-fp=%d" % args.fp, "-pp=%d" % args.pp, "-visc=%d" % args.visc]
     if world > 1:
         cli += ["-mpi=1,1,%d" % world, "-mpi-s=%s" % scaling]
     setup = host.Setup(os.path.join(REPO, "settings", w["json"]), cli, rank=rank, nranks=world)
@@ -383,6 +385,8 @@ def main():
     t_ic = time.time() - t0
 
     eng = capi.Engine(setup.block, setup.thermal, setup.scheme, device=local, keepalive=(setup,))
+    if args.visc:
+        eng.set_transport(setup.transport, keepalive=(setup,))
     ws_gb = eng.L.dll.xf_field_doubles(eng.ctx) * 8 * 6 / 1e9
     if args.host_chunks is not None:
         L.check(L.dll.xf_set_host_overlap(eng.ctx, args.host_chunks))
@@ -565,7 +569,7 @@ def main():
     if rank == 0:
         line = {"metric": "cell-updates/sec (Mcell*stage/s)", "value": value, "unit": "Mcell*stage/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "positivity_preserving": bool(args.pp), "flux_splitting": "LLF",
+                "config": {"workload": w["desc"], "grid_per_gpu": [setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner], "emax": E, "weno": args.weno, "positivity_preserving": bool(args.pp), "flux_splitting": args.alpha, "viscous": bool(args.visc),
                            "fp_mode": "strict (no FMA contraction; parity mode)" if args.fp == 0 else "fast (FMA contraction in sweeps/LU/RK)",
                            "decomposition": "z-slabs x%d, halo = 4 planes of U per face per stage (NCCL send/recv)" % world if world > 1 else "single block",
                            "flush": "working set %.1f GB per GPU >> 126 MB L2, no explicit flush" % ws_gb,

@@ -66,6 +66,19 @@ typedef struct xf_scheme {
 	                          PositivityPreserving_kernels.hpp:5-76, fused into the tail of each sweep */
 } xf_scheme;
 
+/* viscous / heat-conduction / species-diffusion terms.  Compile-time in the reference (Visc, Visc_Heat, Visc_Diffu,
+ * cmake/init_options.cmake:81-92), run-time here; the transport fits are the host's (Setup::GetFitCoefficient, viscfit.cpp:148-190). */
+typedef struct xf_transport {
+	int visc, visc_heat, visc_diffu;
+	const double *fit_visc;    /* host, [num_species*4]  ln(mu_k)     = sum_m c[m] (ln T)^m   (fitted_coefficients_visc)  */
+	const double *fit_therm;   /* host, [num_species*4]  ln(lambda_k)                          (fitted_coefficients_therm) */
+	const double *fit_Dkj;     /* host, [num_species*num_species*4]  ln(p D_kj)                (Dkj_matrix)                */
+	const double *Wi;          /* host, [num_species]  molar masses, kg/mol                    (species_chara[.. + Wi])    */
+	double Yil_limiter, Dim_limiter;   /* Block::Yil_limiter, Block::Dim_limiter (src/read_ini/src/iniset.cpp:358-359) */
+	double dim_max0;           /* Dim_max before scaling: 0.0 = the reference's single-process build (its Dkm reduction is commented
+	                              out, ConVenction_block.hpp:478-479, so the diffusion fluxes are clipped to zero), 1.0 = its MPI build */
+} xf_transport;
+
 typedef struct xf_ctx xf_ctx;
 
 /* ---- life cycle ---------------------------------------------------------------------------- */
@@ -74,6 +87,10 @@ typedef struct xf_ctx xf_ctx;
 int xf_create(const xf_block *bl, const xf_thermal *th, const xf_scheme *sc, int device, xf_ctx **out);
 int xf_destroy(xf_ctx *ctx);
 const char *xf_last_error(void);
+/* switches the viscous terms on (visc != 0) for every later xf_get_lu / xf_rk_stage / xf_run: allocates the velocity-derivative and
+ * transport-coefficient work arrays (21 + 2 num_species scalars per cell) and copies the fits.  The wall fluxes then are
+ * inviscid (+ limiter) - viscous, as in GetLU (ConVenction_block.hpp:424-575). */
+int xf_set_transport(xf_ctx *ctx, const xf_transport *tr);
 int xf_set_stream(xf_ctx *ctx, void *cuda_stream);   /* all later launches go to this stream (default: 0) */
 int xf_synchronize(xf_ctx *ctx);
 

@@ -4,7 +4,8 @@
 # (nothing is copied into this repo) against the host SYCL shim in oracle/shim, once per
 # case/scheme, into oracle/_ref/<case>_w<order>_<mode>/XFLUIDS.   SURVEY.md 8c / Appendix E.
 #
-#   usage: oracle/build_ref.sh <case> <weno 5|6|7> <mode parity|fast> [alpha LLF|GLF|ROE] [pp 0|1]
+#   usage: oracle/build_ref.sh <case> <weno 5|6|7> <mode parity|fast> [alpha LLF|GLF|ROE] [pp 0|1] [visc 0|1]
+#   visc 1 = -DVisc=1 -DVisc_Heat=1 -DVisc_Diffu=1 with the fourth-order viscous discretisation (what init_sample.cmake sets for shock-bubble)
 #   weno 6 = WENO-CU6 (SCHEME_ORDER 6); pp 1 = oracle/cases/<case>_pp.json: equations.PositivityPreserving true at CFL 0.9 (at the cases' CFL 0.4 the limiter
 #   never acts in these flows; at 0.9 it limits from the first step on)
 #   case:  shock-tube | vortex | riemann | sbi | jet
@@ -17,7 +18,7 @@ set -euo pipefail
 REF=${XF_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 REPO=$(cd "$HERE/.." && pwd)
-CASE=$1; WENO=${2:-5}; MODE=${3:-parity}; ALPHA=${4:-LLF}; PP=${5:-0}
+CASE=$1; WENO=${2:-5}; MODE=${3:-parity}; ALPHA=${4:-LLF}; PP=${5:-0}; VISC=${6:-0}
 [ -d "$REF/src" ] || { echo "reference tree $REF not present: cannot build oracle/_ref (prebuilt files are used on the GPU box)"; exit 3; }
 
 case $CASE in
@@ -30,7 +31,7 @@ case $CASE in
 esac
 case $ALPHA in ROE) AT=1;; LLF) AT=2;; GLF) AT=3;; *) echo "bad alpha"; exit 2;; esac
 
-TAG=${CASE}_w${WENO}_${MODE}; [ "$ALPHA" != LLF ] && TAG=${TAG}_${ALPHA}; [ "$PP" = 1 ] && TAG=${TAG}_pp
+TAG=${CASE}_w${WENO}_${MODE}; [ "$ALPHA" != LLF ] && TAG=${TAG}_${ALPHA}; [ "$PP" = 1 ] && TAG=${TAG}_pp; [ "$VISC" = 1 ] && TAG=${TAG}_visc
 OUT=$HERE/_ref/$TAG
 mkdir -p "$OUT/obj" "$OUT/output/cal"
 JSON=$REPO/oracle/cases/$CASE.json
@@ -40,6 +41,7 @@ DEFS=(-D__ACPP__ -DUSE_CXX_BOOST=1 -DUSE_DOUBLE -DSCHEME_ORDER=$WENO -DEIGEN_ALL
       -DESTIM_NAN=1 -DESTIM_OUT=0 -DThermo=1 -DArtificial_type=$AT
       "-DSelectDv=\"host\"" "-DINI_SAMPLE=\"$SAMPLE\"" "-DRFile=\"/runtime.dat/$MIX\"" "-DRPath=\"/runtime.dat\""
       "-DIniFile=\"$JSON\"")
+if [ "$VISC" = 1 ]; then DEFS+=(-DVisc=1 -DVisc_Heat=1 -DVisc_Diffu=1); fi
 if [ $COP = 1 ]; then DEFS+=(-DCOP -DPOSP=0 -DCOP_CHEME=0)
 else DEFS+=(-DPOSP=0 -DNUM_REA=1 -DNUM_COP=0 -DCOP_CHEME=0 -DNUM_SPECIES=1 -DNCOP_Gamma=1.4); fi
 

@@ -50,6 +50,15 @@ int main(int argc, char *argv[])
 		dump_raw(envs("XF_DUMP_DIR") + "/ic_U.bin", fl->d_U, N * Emax * sizeof(real_t));
 		dump_raw(envs("XF_DUMP_DIR") + "/ic_T.bin", fl->d_fstate.T, N * sizeof(real_t));
 	}
+	if (Visc && !envs("XF_DUMP_DIR").empty())
+	{ // transport fits of Setup::GetFitCoefficient (viscfit.cpp:148-190): [NS][4] viscosity, [NS][4] conductivity, [NS*NS][4] binary diffusion,
+	  // and the species characteristics they were made from
+		Thermal &th = setup.h_thermal;
+		dump_raw(envs("XF_DUMP_DIR") + "/fit_visc.bin", th.fitted_coefficients_visc[0], NUM_SPECIES * order_polynominal_fitted * sizeof(real_t));
+		dump_raw(envs("XF_DUMP_DIR") + "/fit_therm.bin", th.fitted_coefficients_therm[0], NUM_SPECIES * order_polynominal_fitted * sizeof(real_t));
+		dump_raw(envs("XF_DUMP_DIR") + "/fit_Dkj.bin", th.Dkj_matrix[0], NUM_SPECIES * NUM_SPECIES * order_polynominal_fitted * sizeof(real_t));
+		dump_raw(envs("XF_DUMP_DIR") + "/species_chara.bin", th.species_chara, NUM_SPECIES * SPCH_Sz * sizeof(real_t));
+	}
 	solver.BoundaryCondition(q);
 	solver.UpdateStates(q);
 
@@ -129,6 +138,16 @@ int main(int argc, char *argv[])
 				dump_raw(ddir + "/s1_Fwx.bin", fl->d_wallFluxF, N * Emax * sizeof(real_t));
 				dump_raw(ddir + "/s1_Fwy.bin", fl->d_wallFluxG, N * Emax * sizeof(real_t));
 				dump_raw(ddir + "/s1_Fwz.bin", fl->d_wallFluxH, N * Emax * sizeof(real_t));
+				if (Visc)
+				{ // intermediates of the viscous block of GetLU (ConVenction_block.hpp:424-575)
+					FlowData &f = fl->d_fstate;
+					dump_raw(ddir + "/s1_visc.bin", f.viscosity_aver, N * sizeof(real_t));
+					dump_raw(ddir + "/s1_therm.bin", f.thermal_conduct_aver, N * sizeof(real_t));
+					dump_raw(ddir + "/s1_Dkm.bin", f.Dkm_aver, N * NUM_SPECIES * sizeof(real_t));
+					dump_raw(ddir + "/s1_hi.bin", f.hi, N * NUM_SPECIES * sizeof(real_t));
+					for (int m = 0; m < 9; m++)
+						dump_raw(ddir + "/s1_Vde" + std::to_string(m) + ".bin", f.Vde[m], N * sizeof(real_t));
+				}
 				error = error || solver.EstimateNAN(q, solver.physicalTime, solver.Iteration, 0, 1);
 				solver.UpdateU(q, 1);
 				dump_raw(ddir + "/s1_U1.bin", fl->d_U1, N * Emax * sizeof(real_t));

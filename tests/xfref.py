@@ -189,22 +189,24 @@ ALPHA_NAME = {1: "ROE", 2: "LLF", 3: "GLF"}
 PP_CFL = 0.9   # CFL of the positivity-preserving variants (oracle/cases/<case>_pp.json)
 
 
-def ref_dir(case, weno=5, mode="parity", alpha=2, pp=0):
+def ref_dir(case, weno=5, mode="parity", alpha=2, pp=0, visc=0):
     tag = "%s_w%d_%s" % (case, weno, mode)
     if alpha != 2:
         tag += "_" + ALPHA_NAME[alpha]
     if pp:
         tag += "_pp"
+    if visc:
+        tag += "_visc"
     return os.path.join(REF_DIR, tag)
 
 
-def ref_available(case, weno=5, mode="parity", alpha=2, pp=0):
-    return os.path.exists(os.path.join(ref_dir(case, weno, mode, alpha, pp), "XFLUIDS"))
+def ref_available(case, weno=5, mode="parity", alpha=2, pp=0, visc=0):
+    return os.path.exists(os.path.join(ref_dir(case, weno, mode, alpha, pp, visc), "XFLUIDS"))
 
 
-def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None, alpha=2, pp=0):
+def run_ref(case, res, nsteps, dump_steps=(), weno=5, mode="parity", stage_dump=False, dump_T=True, outdir=None, threads=None, alpha=2, pp=0, visc=0):
     """Run the compiled reference; returns (dict of arrays, meta dict, stdout)."""
-    d = ref_dir(case, weno, mode, alpha, pp)
+    d = ref_dir(case, weno, mode, alpha, pp, visc)
     out = outdir or tempfile.mkdtemp(prefix="xfref_")
     env = dict(os.environ, XF_NSTEPS=str(nsteps), XF_DUMP_DIR=out, XF_DUMP_STEPS=",".join(map(str, dump_steps)),
                XF_DUMP_STAGE="1" if stage_dump else "0", XF_DUMP_T="1" if dump_T else "0")

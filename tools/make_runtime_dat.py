@@ -39,9 +39,20 @@ def main(src, dst):
             f.write("*%s\n" % s)
             f.writelines(b[s])
         f.write("*END\n")
-    # files the reference parser opens unconditionally (thermal.cpp:96,137); inviscid NASA runs read nothing from them
+    # Lennard-Jones transport parameters (GRI-Mech transport data as shipped by the reference; parser: thermal.cpp:131-165) for the
+    # species carried here, and the Monchick-Mason collision-integral table the transport fits interpolate in (viscfit.cpp:330-350)
     with open(os.path.join(dst, "transport_data.dat"), "w") as f:
-        f.write("! Lennard-Jones transport parameters are not used by the inviscid path; the parser only needs the terminator\n*END\n")
+        f.write("# xfluids-b200 runtime.dat: Lennard-Jones transport parameters (GRI-Mech 3.0 transport data), XFluids format:\n")
+        f.write("# Species  geo  eps/kB(K)  sigma(ang)  mue(Debye)  alpha(ang^3)  Zrot@298K ; the list ends with a star+END line\n")
+        seen = set()
+        for line in open(os.path.join(src, "transport_data.dat")):
+            t = line.split()
+            if t and t[0] in SPECIES and t[0] not in seen:
+                seen.add(t[0])
+                f.write(line.split("!")[0].rstrip() + "\n")
+        f.write("*END\n")
+    with open(os.path.join(src, "collision_integral.dat")) as fi, open(os.path.join(dst, "collision_integral.dat"), "w") as fo:
+        fo.write(fi.read())
     with open(os.path.join(dst, "thermal_dynamics_janaf.dat"), "w") as f:
         f.write("! JANAF/NASA-7 tables are not used (Thermo=1, NASA-9); the parser only needs the terminator\n*END\n")
     for m in MIXTURES:

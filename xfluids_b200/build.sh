@@ -18,7 +18,7 @@ stale() { # stale <target> <deps...>
   for d in "$@"; do [ "$d" -nt "$t" ] && return 0; done
   return 1
 }
-KDEPS="$SRC/xf_kernels.cu $SRC/xf_math.cuh $SRC/xf_march.cuh $SRC/xf_tma.cuh $SRC/xf_log.cuh $SRC/xf_log_data.h $SRC/xf_types.h $SRC/xf_launch.h"
+KDEPS="$SRC/xf_kernels.cu $SRC/xf_math.cuh $SRC/xf_march.cuh $SRC/xf_visc.cuh $SRC/xf_tma.cuh $SRC/xf_log.cuh $SRC/xf_log_data.h $SRC/xf_types.h $SRC/xf_launch.h"
 pids=()
 if stale "$OBJ/xf_kernels_strict.o" $KDEPS; then nvcc $COMMON -DXF_NS=xf_strict -fmad=false -c "$SRC/xf_kernels.cu" -o "$OBJ/xf_kernels_strict.o" & pids+=($!); fi
 if stale "$OBJ/xf_kernels_fast.o" $KDEPS; then nvcc $COMMON -DXF_NS=xf_fast -fmad=true -c "$SRC/xf_kernels.cu" -o "$OBJ/xf_kernels_fast.o" & pids+=($!); fi

@@ -27,6 +27,11 @@ class XfThermal(C.Structure):
                 ("Hia", C.POINTER(C.c_double)), ("Hib", C.POINTER(C.c_double)), ("Ri", C.POINTER(C.c_double)), ("_Wi", C.POINTER(C.c_double))]
 
 
+class XfTransport(C.Structure):
+    _fields_ = [("visc", C.c_int), ("visc_heat", C.c_int), ("visc_diffu", C.c_int), ("fit_visc", C.POINTER(C.c_double)), ("fit_therm", C.POINTER(C.c_double)),
+                ("fit_Dkj", C.POINTER(C.c_double)), ("Wi", C.POINTER(C.c_double)), ("Yil_limiter", C.c_double), ("Dim_limiter", C.c_double), ("dim_max0", C.c_double)]
+
+
 class XfScheme(C.Structure):
     _fields_ = [("weno_order", C.c_int), ("artificial_type", C.c_int), ("fp_mode", C.c_int), ("positivity", C.c_int)]
 
@@ -40,6 +45,7 @@ _PROTOS = {
     "xf_create": (C.c_int, [C.POINTER(XfBlock), C.POINTER(XfThermal), C.POINTER(XfScheme), C.c_int, C.POINTER(_P)]),
     "xf_destroy": (C.c_int, [_P]),
     "xf_last_error": (C.c_char_p, []),
+    "xf_set_transport": (C.c_int, [_P, C.POINTER(XfTransport)]),
     "xf_set_stream": (C.c_int, [_P, _P]),
     "xf_synchronize": (C.c_int, [_P]),
     "xf_pitch": (C.c_size_t, [_P]),
@@ -180,6 +186,11 @@ class Engine:
         self.U, self.U1, self.LU = _P(), _P(), _P()
         for f in (self.U, self.U1, self.LU):
             self.L.check(self.L.dll.xf_field_alloc(self.ctx, C.byref(f)))
+
+    def set_transport(self, tr, keepalive=()):
+        """Viscous / heat-conduction / species-diffusion terms on (xf_set_transport); tr: XfTransport (host.Setup.transport)."""
+        self._keep = self._keep + (tr,) + tuple(keepalive)
+        self.L.check(self.L.dll.xf_set_transport(self.ctx, C.byref(tr)))
 
     # ---- state I/O in the reference's AoS layout -------------------------------------------------
     def upload(self, field, aos):

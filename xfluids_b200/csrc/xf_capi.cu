@@ -52,16 +52,17 @@ struct XfTable
 	decltype(&xf_strict::launch_halo) halo;
 	decltype(&xf_strict::launch_sweep_x) sweep_x;
 	decltype(&xf_strict::launch_march) march;
+	decltype(&xf_strict::launch_visc) visc;
 };
 static const XfTable T_STRICT = {xf_strict::launch_prim, xf_strict::launch_sweeps, xf_strict::launch_lu, xf_strict::launch_rk, xf_strict::launch_nan,
 								 xf_strict::launch_bc, xf_strict::launch_dt, xf_strict::launch_dt_final, xf_strict::launch_layout,
-								 xf_strict::launch_scalar_pad, xf_strict::launch_halo, xf_strict::launch_sweep_x, xf_strict::launch_march};
+								 xf_strict::launch_scalar_pad, xf_strict::launch_halo, xf_strict::launch_sweep_x, xf_strict::launch_march, xf_strict::launch_visc};
 // fast mode: FMA contraction in the sweeps / LU / RK only.  Primitive recovery stays strict: its Newton loop stops on an
 // absolute tolerance and is capped/limited, so a 1-ulp difference can change the trip count and move T by O(1e-6)
 // (measured: 2e-6 relative on U after one jet step with a contracted prim kernel).
 static const XfTable T_FAST = {xf_strict::launch_prim, xf_fast::launch_sweeps, xf_fast::launch_lu, xf_fast::launch_rk, xf_fast::launch_nan,
 							   xf_fast::launch_bc, xf_fast::launch_dt, xf_fast::launch_dt_final, xf_fast::launch_layout,
-							   xf_fast::launch_scalar_pad, xf_fast::launch_halo, xf_fast::launch_sweep_x, xf_fast::launch_march};
+							   xf_fast::launch_scalar_pad, xf_fast::launch_halo, xf_fast::launch_sweep_x, xf_fast::launch_march, xf_fast::launch_visc};
 
 struct xf_ctx
 {
@@ -72,6 +73,7 @@ struct xf_ctx
 	int ns = 1, cop = 0, ghost = 0, E = 5;
 	XfDev d{};
 	XfThermo th{};
+	XfVisc vs{};
 	const XfTable *t = nullptr;
 	std::vector<void *> owned;      // device allocations freed in xf_destroy
 	double *stage = nullptr;        // device staging for AoS import/export [Ncells*E]
@@ -94,6 +96,7 @@ struct xf_ctx
 	// TMA-fed marching sweeps with the divergence / update fused in (xf_march.cuh) -- bit-identical results, measured slower on every
 	// BASELINE config (profiles/r02_tuning.md), kept selectable for that A/B
 	int tiled = 1;
+	int gbc_stage[6] = {0, 0, 0, 0, 0, 0}; // face conditions of the stage in flight (the viscous block needs them for the derivative ghost fill)
 	size_t ncells() const { return size_t(bl.Xmax) * bl.Ymax * bl.Zmax; }
 };
 
@@ -367,6 +370,16 @@ extern "C"
 		if (!std::strcmp(name, "c")) return d.c;
 		if (c->cop && name[0] == 'y' && name[1] >= '0' && name[1] < '0' + c->ns && !name[2])
 			return d.y + (size_t)(name[1] - '0') * d.N;
+		// viscous work arrays (after xf_set_transport): "visc", "therm", "Vde<0..8>", "Dkm<k>", "hi<k>"
+		const XfVisc &v = c->vs;
+		if (v.on && v.Vde)
+		{
+			if (!std::strcmp(name, "visc")) return v.va;
+			if (!std::strcmp(name, "therm")) return v.tca;
+			if (!std::strncmp(name, "Vde", 3) && name[3] >= '0' && name[3] <= '8' && !name[4]) return v.Vde + (size_t)(name[3] - '0') * d.N;
+			if (!std::strncmp(name, "Dkm", 3) && name[3] >= '0' && name[3] < '0' + c->ns && !name[4]) return v.Dkm + (size_t)(name[3] - '0') * d.N;
+			if (!std::strncmp(name, "hi", 2) && name[2] >= '0' && name[2] < '0' + c->ns && !name[3]) return v.hi + (size_t)(name[2] - '0') * d.N;
+		}
 		return nullptr;
 	}
 	int xf_set_scalar(xf_ctx *c, const char *name, const double *h)
@@ -408,6 +421,7 @@ extern "C"
 	int xf_boundary(xf_ctx *c, double *U, const int bc[6])
 	{
 		XF_DEVICE(c);
+		std::memcpy(c->gbc_stage, bc, 6 * sizeof(int));
 		KL(c->t->bc(c->d, c->E, c->cop, U, bc, c->stream, &c->launches, 7, -1, -1));
 		return XF_OK;
 	}
@@ -444,6 +458,53 @@ extern "C"
 					cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
 			}
 		return 0;
+	}
+
+	int xf_set_transport(xf_ctx *c, const xf_transport *tr)
+	{
+		XF_DEVICE(c);
+		if (!tr)
+			return fail(XF_ERR_ARG, "null transport");
+		XfVisc &v = c->vs;
+		const bool was_on = v.on != 0;
+		double *keep[5] = {v.Vde, v.va, v.tca, v.Dkm, v.hi};
+		double *keep_lim = v.lim;
+		std::memset(&v, 0, sizeof(v));
+		v.Vde = keep[0], v.va = keep[1], v.tca = keep[2], v.Dkm = keep[3], v.hi = keep[4], v.lim = keep_lim;
+		v.on = tr->visc ? 1 : 0, v.heat = (tr->visc && tr->visc_heat) ? 1 : 0, v.diffu = (tr->visc && tr->visc_diffu) ? 1 : 0;
+		if (c->gexec) // the parameter block travels by value inside captured launches
+			cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+		if (!v.on)
+			return XF_OK;
+		if (!c->tiled)
+			return fail(XF_ERR_ARG, "the viscous terms need the wall fluxes in memory: not with XF_MARCH=1");
+		if (!tr->fit_visc || !tr->Wi || (v.heat && !tr->fit_therm) || (v.diffu && !tr->fit_Dkj))
+			return fail(XF_ERR_ARG, "transport fits missing");
+		const int ns = c->ns;
+		for (int n = 0; n < ns; n++)
+		{
+			for (int m = 0; m < 4; m++)
+			{
+				v.fit_visc[n][m] = tr->fit_visc[n * 4 + m];
+				if (v.heat)
+					v.fit_therm[n][m] = tr->fit_therm[n * 4 + m];
+			}
+			v.Wi[n] = tr->Wi[n];
+			if (v.diffu)
+				for (int q = 0; q < ns; q++)
+					for (int m = 0; m < 4; m++)
+						v.fit_Dkj[n * ns + q][m] = tr->fit_Dkj[(n * ns + q) * 4 + m];
+		}
+		v.Yil_limiter = tr->Yil_limiter, v.Dim_limiter = tr->Dim_limiter, v.dim_max0 = tr->dim_max0;
+		if (!was_on || !v.Vde)
+		{
+			const size_t N = (size_t)c->d.N;
+			int rc;
+			if ((!v.Vde && (rc = dmalloc(c, &v.Vde, 9 * N))) || (!v.va && (rc = dmalloc(c, &v.va, N))) || (!v.tca && (rc = dmalloc(c, &v.tca, N))) ||
+				(!v.Dkm && (rc = dmalloc(c, &v.Dkm, N * ns))) || (!v.hi && (rc = dmalloc(c, &v.hi, N * ns))) || (!v.lim && (rc = dmalloc(c, &v.lim, 4 * XF_MAXS))))
+				return rc;
+		}
+		return ensure_fw(c);
 	}
 
 	// ---- TMA tensor maps of the marching sweeps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
@@ -571,6 +632,10 @@ extern "C"
 				return rc;
 			if (finish)
 			{
+				if (c->vs.on)
+				{ // viscous wall fluxes are subtracted once every direction's inviscid wall flux is in memory (ConVenction_block.hpp:424-575)
+					KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches));
+				}
 				KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 				c->launches++;
 			}
@@ -690,6 +755,8 @@ extern "C"
 				c->launches++;
 			}
 		}
+		if (c->vs.on)
+			KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, U, c->gbc_stage, c->stream, &c->launches));
 		KL(c->t->lu(c->d, c->E, LU, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -1120,7 +1187,7 @@ extern "C"
 	static bool host_overlap_ok(xf_ctx *c)
 	{
 		const XfDev &d = c->d;
-		return c->host_chunks > 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks && c->sc.artificial_type != 3;
+		return !c->vs.on && c->host_chunks > 1 && d.DimX && d.DimY && d.DimZ && d.Zmax >= 6 * d.Bz && d.Zmax >= c->host_chunks && c->sc.artificial_type != 3;
 	}
 	int xf_host_begin(xf_ctx *c, double *h_U, const int bc[6], double t_end, double *U, double *U1, double *LU)
 	{

@@ -1032,6 +1032,8 @@ __global__ void __launch_bounds__(256) k_halo(XfDev d, double *__restrict__ U, d
 			return (int)e__;                      \
 	} while (0)
 
+#include "xf_visc.cuh"
+
 template <class C>
 static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1)
 {
@@ -1218,6 +1220,10 @@ int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t
 	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz));
 }
 int z_tile_faces() { return XF_TF; }
+int launch_visc(const XfDev &d, const XfThermo &th, const XfVisc &vs, int ns, int cop, const double *U, const int bc[6], cudaStream_t s, long long *launches)
+{
+	XF_DISPATCH_CFG(ns, cop, return visc_t<C>(d, th, vs, U, bc, s, launches));
+}
 int launch_sweep_x(const XfDev &d, int ns, int cop, const double *U, const XfMarchArgs &a, cudaStream_t s)
 {
 	XF_DISPATCH_CFG(ns, cop, return sweep_x_t<C>(d, U, a, s));

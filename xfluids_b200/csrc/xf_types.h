@@ -69,6 +69,23 @@ struct XfDev
 	unsigned *hard_ids, *hard_count;   // cells whose Newton iteration needs more than XF_NEWTON_FAST steps (k_prim -> k_prim_hard)
 };
 
+// viscous / heat-conduction / species-diffusion terms (reference: solver_Reconstruction/viscosity/**; Visc, Visc_Heat, Visc_Diffu of
+// cmake/init_options.cmake:81-92 made run-time).  Transport fits of Setup::GetFitCoefficient (viscfit.cpp:148-190): cubic polynomials in ln T.
+struct XfVisc
+{
+	int on, heat, diffu;
+	double fit_visc[XF_MAXS][4], fit_therm[XF_MAXS][4]; // ln(mu_k), ln(lambda_k)
+	double fit_Dkj[XF_MAXS * XF_MAXS][4];               // ln(p D_kj)
+	double Wi[XF_MAXS];                                 // kg/mol
+	double Yil_limiter, Dim_limiter, dim_max0;          // Block::Yil_limiter / Dim_limiter (iniset.cpp:358-359); Dim_max before scaling (0: the single-process build's value)
+	// work arrays
+	double *Vde;   // [9][N] velocity derivatives, order ducx dvcx dwcx ducy dvcy dwcy ducz dvcz dwcz (global_setup.h VdeType)
+	double *va, *tca; // [N] mixture viscosity, thermal conductivity
+	double *Dkm;   // [NS][N] mixture-averaged diffusion coefficients
+	double *hi;    // [NS][N] species enthalpies
+	double *lim;   // device doubles: [0..NS) yi_min, [NS..2NS) yi_max -> after k_visc_limits: [2NS..3NS) Yil_limiter, [3NS..4NS) Diffu_limiter
+};
+
 // arguments of one sweep launch beyond the block description (k_sweep x direction, k_march y / z)
 struct XfMarchArgs
 {

@@ -6,13 +6,13 @@ import os
 
 import numpy as np
 
-from .capi import XfBlock, XfScheme, XfThermal, XfError, Lib
+from .capi import XfBlock, XfScheme, XfThermal, XfTransport, XfError, Lib
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
 _P = C.c_void_p
 
-HOST_SYMBOLS = ["xfh_last_error", "xfh_setup_create", "xfh_setup_destroy", "xfh_setup_block", "xfh_setup_thermal", "xfh_setup_scheme",
+HOST_SYMBOLS = ["xfh_last_error", "xfh_setup_create", "xfh_setup_destroy", "xfh_setup_block", "xfh_setup_thermal", "xfh_setup_scheme", "xfh_setup_transport",
                 "xfh_setup_bc", "xfh_setup_info", "xfh_setup_stamps", "xfh_setup_ini", "xfh_initial_condition", "xfh_solver_create",
                 "xfh_solver_destroy", "xfh_solver_init", "xfh_solver_evolve", "xfh_solver_download", "xfh_solver_checkpoint",
                 "xfh_solver_ctx", "xfh_solver_fields"]
@@ -38,6 +38,7 @@ class HostLib:
         d.xfh_setup_block.argtypes = [_P, C.POINTER(XfBlock)]
         d.xfh_setup_thermal.argtypes = [_P, C.POINTER(XfThermal)]
         d.xfh_setup_scheme.argtypes = [_P, C.POINTER(XfScheme)]
+        d.xfh_setup_transport.argtypes = [_P, C.POINTER(XfTransport)]
         d.xfh_setup_bc.argtypes = [_P, C.c_int * 6]
         d.xfh_setup_info.argtypes = [_P, C.c_int * 8]
         d.xfh_setup_stamps.argtypes = [_P, _P]
@@ -77,6 +78,8 @@ class Setup:
         self.H.dll.xfh_setup_block(self.h, C.byref(self.block))
         self.H.dll.xfh_setup_thermal(self.h, C.byref(self.thermal))
         self.H.dll.xfh_setup_scheme(self.h, C.byref(self.scheme))
+        self.transport = XfTransport()
+        self.H.dll.xfh_setup_transport(self.h, C.byref(self.transport))
         bc, info = (C.c_int * 6)(), (C.c_int * 8)()
         self.H.dll.xfh_setup_bc(self.h, bc)
         self.H.dll.xfh_setup_info(self.h, info)

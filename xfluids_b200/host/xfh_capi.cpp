@@ -29,6 +29,7 @@ extern "C"
 	void xfh_setup_block(void *s, xf_block *b) { *b = ((Setup *)s)->bl; }
 	void xfh_setup_thermal(void *s, xf_thermal *t) { *t = ((Setup *)s)->thermal(); }
 	void xfh_setup_scheme(void *s, xf_scheme *sc) { *sc = ((Setup *)s)->scheme(); }
+	void xfh_setup_transport(void *s, xf_transport *t) { *t = ((Setup *)s)->transport(); }
 	void xfh_setup_bc(void *s, int bc[6]) { ((Setup *)s)->rank_boundarys(bc); }
 	// info[0..7] = Emax, num_species, cop, ghost_species, nStepmax, mz, myMpiPos_z, n_stamps
 	void xfh_setup_info(void *s_, int info[8])

@@ -21,6 +21,11 @@ namespace xfh
 		xf_thermal th = Fs.thermal();
 		xf_scheme sc = Fs.scheme();
 		XFCK(xf_create(&Fs.bl, &th, &sc, device, &ctx));
+		if (Fs.Visc)
+		{
+			xf_transport tr = Fs.transport();
+			XFCK(xf_set_transport(ctx, &tr));
+		}
 		Fs.rank_boundarys(BCs);
 	}
 	Fluid::~Fluid()

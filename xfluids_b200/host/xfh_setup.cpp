@@ -38,6 +38,8 @@ namespace xfh
 		j_conf = ReadJson(json_path);
 		ReWrite();
 		ReadSpecies();
+		if (Visc)
+			GetFitCoefficient(); // constructor.cpp:36-38
 		init();
 		// MpiTrans::MpiTrans (mpiPacks.cpp:3-75): position of this rank in the process grid; only z-slabs here
 		if (mx != 1 || my != 1)
@@ -64,6 +66,9 @@ namespace xfh
 		RcalInterval = int(run.value("RcalInterval", 100.0));
 		RSources = eq.value("Sources_React", false);
 		PositivityPreserving = eq.value("PositivityPreserving", false);
+		Tnode = eq.value("ViscosityFittingTnode", Tnode);                    // read_json.cpp:70
+		Yil_limiter_json = mesh.value("Yil_limiter", 1.0E10), Dim_limiter_json = mesh.value("Dim_limiter", 2.0E-3); // read_json.cpp:104-105
+		Visc = b2.value("visc", 0.0) != 0.0, Visc_Heat = b2.value("visc_heat", Visc ? 1.0 : 0.0) != 0.0, Visc_Diffu = b2.value("visc_diffu", Visc ? 1.0 : 0.0) != 0.0;
 		mx = int(mpi.value("mx", 1.0)), my = int(mpi.value("my", 1.0)), mz = int(mpi.value("mz", 1.0));
 
 		bl.CFLnumber = run.value("CFLnumber", 0.4);
@@ -161,6 +166,10 @@ namespace xfh
 		if (!match("-fp").empty()) fp_mode = std::atoi(match("-fp")[0].c_str());
 		if (!match("-pp").empty()) PositivityPreserving = std::atoi(match("-pp")[0].c_str()) != 0;
 		if (!match("-cfl").empty()) bl.CFLnumber = std::atof(match("-cfl")[0].c_str());
+		if (!match("-visc").empty()) Visc = Visc_Heat = Visc_Diffu = std::atoi(match("-visc")[0].c_str()) != 0;
+		if (!match("-visc-heat").empty()) Visc_Heat = std::atoi(match("-visc-heat")[0].c_str()) != 0;
+		if (!match("-visc-diffu").empty()) Visc_Diffu = std::atoi(match("-visc-diffu")[0].c_str()) != 0;
+		if (!match("-diffu-mpi").empty()) diffu_dim_max0 = std::atoi(match("-diffu-mpi")[0].c_str()) != 0 ? 1.0 : 0.0;
 		std::vector<int> bcv = ints("-bc"); // run-time override of mesh.Boundarys (xmin, xmax, ymin, ymax, zmin, zmax; BConditions codes)
 		if (bcv.size() == 6)
 			for (int i = 0; i < 6; i++)
@@ -308,6 +317,9 @@ namespace xfh
 		if (bl.DimY) dl = std::min(dl, bl.dy);
 		if (bl.DimZ) dl = std::min(dl, bl.dz);
 		bl._dx = 1.0 / bl.dx, bl._dy = 1.0 / bl.dy, bl._dz = 1.0 / bl.dz;
+		// robust limiters of the species-diffusion flux (iniset.cpp:358-359)
+		Dim_limiter = std::min(std::max(Dim_limiter_json, 0.0), 1.0);
+		Yil_limiter = std::max(std::max(bl._dx, bl._dy), bl._dz) * std::min(std::max(Yil_limiter_json, 0.0), 1.0);
 		ini._xa2 = 1.0 / (ini.xa * ini.xa);
 		ini._yb2 = 1.0 / (ini.yb * ini.yb);
 		ini._zc2 = 1.0 / (ini.zc * ini.zc);

@@ -7,6 +7,7 @@
 // is run-time here: optional JSON section "b200" {sample, mixture, weno, artificial, fp_mode} or -sample= -mixture=
 // -weno= -alpha= -fp= -pp= -cfl= on the command line (-pp overrides equations.PositivityPreserving, -cfl run.CFLnumber).  The reference ignores unknown JSON keys, so files stay interchangeable.
 #pragma once
+#include <array>
 #include <string>
 #include <vector>
 #include "../../include/xfluids_b200.h"
@@ -58,6 +59,13 @@ namespace xfh
 		double dl = 0;
 		int Boundarys[6] = {2, 2, 2, 2, 2, 2};
 		bool RSources = false, PositivityPreserving = false;
+		// viscous terms: Visc / Visc_Heat / Visc_Diffu are compile-time in the reference (cmake/init_options.cmake:81-92; shock-bubble preset:
+		// all three ON, fourth-order discretisation), run-time here: JSON "b200": {"visc": 1, "visc_heat": 1, "visc_diffu": 1} or -visc=0|1
+		// (all three), -visc-heat=, -visc-diffu= on the command line.  -diffu-mpi=1 selects the reference MPI build's diffusion limiter.
+		bool Visc = false, Visc_Heat = false, Visc_Diffu = false;
+		double Yil_limiter = 0, Dim_limiter = 0, Yil_limiter_json = 1.0E10, Dim_limiter_json = 2.0E-3, diffu_dim_max0 = 0.0;
+		std::vector<double> Tnode{273.15, 500.0, 750.0, 1000.0, 1250.0, 1500.0, 1750.0, 2000.0, 2250.0, 2500.0, 2750.0, 3000.0, 5000.0};
+		std::vector<double> species_chara, fit_visc, fit_therm, fit_Dkj; // [NS*9], [NS*4], [NS*4], [NS*NS*4]
 		size_t bytes = 0, cellbytes = 0;
 
 		// ---- fluids
@@ -80,6 +88,8 @@ namespace xfh
 		void ReadThermal();  // thermal.cpp:36-175
 		void init();         // iniset.cpp:290-369
 		bool Mach_Shock();   // viscfit.cpp:8-140
+		void GetFitCoefficient(); // viscfit.cpp:148-190 + the transport part of ReadThermal (thermal.cpp:131-165)
+		xf_transport transport() const;
 		void print() const;
 
 		xf_thermal thermal() const;
