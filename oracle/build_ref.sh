@@ -5,6 +5,7 @@
 # case/scheme, into oracle/_ref/<case>_w<order>_<mode>/XFLUIDS.   SURVEY.md 8c / Appendix E.
 #
 #   usage: oracle/build_ref.sh <case> <weno 5|6|7> <mode parity|fast> [alpha LLF|GLF|ROE] [pp 0|1] [visc 0|1]
+#   out 1 (7th) = oracle/cases/<case>_out.json: OutDAT / OutVTI on and one output stamp per format (common / compressed / partial)
 #   visc 1 = -DVisc=1 -DVisc_Heat=1 -DVisc_Diffu=1 with the fourth-order viscous discretisation (what init_sample.cmake sets for shock-bubble)
 #   weno 6 = WENO-CU6 (SCHEME_ORDER 6); pp 1 = oracle/cases/<case>_pp.json: equations.PositivityPreserving true at CFL 0.9 (at the cases' CFL 0.4 the limiter
 #   never acts in these flows; at 0.9 it limits from the first step on)
@@ -18,7 +19,7 @@ set -euo pipefail
 REF=${XF_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 REPO=$(cd "$HERE/.." && pwd)
-CASE=$1; WENO=${2:-5}; MODE=${3:-parity}; ALPHA=${4:-LLF}; PP=${5:-0}; VISC=${6:-0}
+CASE=$1; WENO=${2:-5}; MODE=${3:-parity}; ALPHA=${4:-LLF}; PP=${5:-0}; VISC=${6:-0}; OUTJ=${7:-0}
 [ -d "$REF/src" ] || { echo "reference tree $REF not present: cannot build oracle/_ref (prebuilt files are used on the GPU box)"; exit 3; }
 
 case $CASE in
@@ -31,10 +32,11 @@ case $CASE in
 esac
 case $ALPHA in ROE) AT=1;; LLF) AT=2;; GLF) AT=3;; *) echo "bad alpha"; exit 2;; esac
 
-TAG=${CASE}_w${WENO}_${MODE}; [ "$ALPHA" != LLF ] && TAG=${TAG}_${ALPHA}; [ "$PP" = 1 ] && TAG=${TAG}_pp; [ "$VISC" = 1 ] && TAG=${TAG}_visc
+TAG=${CASE}_w${WENO}_${MODE}; [ "$ALPHA" != LLF ] && TAG=${TAG}_${ALPHA}; [ "$PP" = 1 ] && TAG=${TAG}_pp; [ "$VISC" = 1 ] && TAG=${TAG}_visc; [ "$OUTJ" = 1 ] && TAG=${TAG}_out
 OUT=$HERE/_ref/$TAG
 mkdir -p "$OUT/obj" "$OUT/output/cal"
 JSON=$REPO/oracle/cases/$CASE.json
+if [ "$OUTJ" = 1 ]; then JSON=$REPO/oracle/cases/${CASE}_out.json; fi   # field output on (OutDAT, OutVTI) with several output formats
 if [ "$PP" = 1 ]; then JSON=$REPO/oracle/cases/${CASE}_pp.json; [ -f "$JSON" ] || { echo "no $JSON"; exit 2; }; fi
 
 DEFS=(-D__ACPP__ -DUSE_CXX_BOOST=1 -DUSE_DOUBLE -DSCHEME_ORDER=$WENO -DEIGEN_ALLOC=0 -D__SYNC_TIMER_=1

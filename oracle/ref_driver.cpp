@@ -16,6 +16,8 @@
 //                          primitives after UpdateStates, LU + wall fluxes after ComputeLU
 //   XF_DUMP_IC=1           dump ic_U / ic_T: the raw initial condition before BC + UpdateStates
 //   XF_DUMP_T=1            dump T (the Newton warm-start state) with every U dump
+//   XF_OUTPUT=<n>          after the loop, write the reference's field output (XFLUIDS::Output) of the final state in the format
+//                          of output stamp number n into ./output
 // Prints one line "ORACLE_TIMING ..." with the wall time of the time loop.
 #include "global_class.h"
 #include <chrono>
@@ -171,6 +173,13 @@ int main(int argc, char *argv[])
 				break;
 			}
 		}
+	}
+	if (!envs("XF_OUTPUT").empty())
+	{ // one field output of the final state in the format of output stamp number XF_OUTPUT (XFLUIDS.cpp:309 does this with the last stamp)
+		// (XFLUIDS keeps a private COPY of Setup, whose stamps AllocateMemory initialised, XFLUIDS.cpp:611-612; the same public call here)
+		const size_t which = std::min<size_t>(std::atoi(envs("XF_OUTPUT").c_str()), setup.OutTimeStamps.size() - 1);
+		setup.OutTimeStamps[which].Initialize(setup.BlSz, setup.species_name, fl->h_fstate);
+		solver.Output(q, setup.OutTimeStamps[which].Reinitialize(solver.physicalTime, std::to_string(solver.Iteration)));
 	}
 	double secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
 	double cells = double(bl.X_inner) * bl.Y_inner * bl.Z_inner;

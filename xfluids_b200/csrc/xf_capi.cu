@@ -368,6 +368,9 @@ extern "C"
 		if (!std::strcmp(name, "w")) return d.w;
 		if (!std::strcmp(name, "H")) return d.H;
 		if (!std::strcmp(name, "c")) return d.c;
+		if (!std::strcmp(name, "rho") && c->lastUI) return const_cast<double *>(c->lastUI); // component 0 of the field the primitives were derived from
+		if (!std::strncmp(name, "UI", 2) && name[2] >= '0' && name[2] < '0' + c->E && !name[3] && c->lastUI) // component n of that field
+			return const_cast<double *>(c->lastUI) + (size_t)(name[2] - '0') * d.N;
 		if (c->cop && name[0] == 'y' && name[1] >= '0' && name[1] < '0' + c->ns && !name[2])
 			return d.y + (size_t)(name[1] - '0') * d.N;
 		// viscous work arrays (after xf_set_transport): "visc", "therm", "Vde<0..8>", "Dkm<k>", "hi<k>"

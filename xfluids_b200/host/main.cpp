@@ -1,7 +1,8 @@
 // xfluids_b200 executable: the reference's src/main.cpp flow (main.cpp:30-54) on the CUDA engine.
 //   xfluids <settings.json> [-run=nx,ny,nz[,nsteps]] [-sample=..] [-mixture=..] [-weno=5|6|7] [-alpha=LLF|GLF|ROE]
 //           [-fp=0|1] [-pp=0|1] [-cfl=x] [-bc=a,b,c,d,e,f] [-dev=n] [-blocks] [-ckpt=path] [-restart=path] [-quiet]
-//           [-mpi=1,1,N -mpi-s=weak|strong]
+//           [-mpi=1,1,N -mpi-s=weak|strong] [-out [-outdir=dir] [-dv=name]] [-visc=0|1]
+// -out writes the reference's field files (VTI / CVTI .vti + .pvti, CPLT .dat) as run.OutDAT / OutVTI and the output stamps ask.
 // -ckpt writes the reference's CheckingPoint format at the end, -restart continues from such a file (XFLUIDS.cpp:616-623,689-724).
 // -mpi=1,1,N: N z-slabs on the GPUs dev .. dev+N-1 of this box.  Where the reference starts N MPI processes (mpiPacks.cpp:3-75), this
 // executable runs one host thread per GPU in ONE process; the ranks talk through the NCCL slab stepper of the CUDA library (halo
@@ -35,6 +36,7 @@ struct Options
 	bool fused = true, quiet = false;
 	std::string ckpt, restart;
 	int nranks = 1;
+	bool output = false; // -out: write the field files of run.OutDAT / OutVTI at the output stamps (off by default: benchmarks)
 };
 
 struct RankResult
@@ -63,6 +65,8 @@ static void run_rank(const char *json, const std::vector<std::string> &cli, cons
 			solver.AttachSlab(comm);
 		}
 		solver.AllocateMemory();
+		if (o.output)
+			solver.EnableOutput();
 		solver.InitialCondition();
 		const std::string suffix = o.nranks > 1 ? ".rank" + std::to_string(rank) : "";
 		if (!o.restart.empty() && !solver.Read_Ubak(o.restart + suffix))
@@ -103,6 +107,7 @@ int main(int argc, char *argv[])
 			if (!a.compare(0, 5, "-dev=")) o.device = std::atoi(a.c_str() + 5);
 			if (a == "-blocks") o.fused = false;
 			if (a == "-quiet") o.quiet = true;
+			if (a == "-out") o.output = true;
 			if (!a.compare(0, 6, "-ckpt=")) o.ckpt = a.substr(6);
 			if (!a.compare(0, 9, "-restart=")) o.restart = a.substr(9);
 			if (!a.compare(0, 5, "-mpi="))

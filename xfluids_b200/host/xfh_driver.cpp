@@ -154,26 +154,43 @@ namespace xfh
 		return RungeKuttaSP3rd(3);
 	}
 
+	void XFLUIDS::EnableOutput() { out.reset(new FieldOutput(*this)); }
+
 	bool XFLUIDS::Evolution(bool fused)
 	{
 		Fluid &f = *fluids[0];
 		bool error_out = false;
 		size_t TimeLoop = 0;
+		// output cadence of XFLUIDS::Evolution (XFLUIDS.cpp:105-183): at Iteration % OutInterval == 0 and after every output stamp, at most
+		// nOutMax + 1 times; then once more at the end (XFLUIDS.cpp:309)
+		const Json &run = Ss.j_conf.at("run");
+		const int OutInterval = std::max(1, int(run.value("OutInterval", double(Ss.nStepmax_json)))), nOutput = int(run.value("nOutMax", 0.0));
+		int OutNum = 0;
+		bool TimeLoopOut = false;
 		XFCK(xf_synchronize(f.ctx));
 		auto t0 = std::chrono::high_resolution_clock::now();
 		while (TimeLoop < Ss.OutTimeStamps.size())
 		{
 			const double target_t = (physicalTime < Ss.OutTimeStamps[TimeLoop].time) ? Ss.OutTimeStamps[TimeLoop].time : Ss.OutTimeStamps[TimeLoop++].time;
+			const OutStamp &OutAtThis = Ss.OutTimeStamps[TimeLoop > 0 ? TimeLoop - 1 : 0];
 			if (fused)
 			{
-				if (physicalTime < target_t && Iteration < Ss.nStepmax)
+				while (physicalTime < target_t && Iteration < Ss.nStepmax)
 				{
+					if (out && ((Iteration % OutInterval == 0) || TimeLoopOut) && OutNum <= nOutput)
+					{
+						OutNum++, TimeLoopOut = false;
+						out->output(OutAtThis.spec, physicalTime, std::to_string(Iteration));
+					}
 					int done = 0, err = 0;
+					// (with field output on, a batch ends where the next Iteration % OutInterval == 0 output is due)
+					const int until_out = out ? OutInterval - Iteration % OutInterval : Ss.nStepmax;
+					const int nrun = std::min(Ss.nStepmax - Iteration, until_out);
 					XFCK(xf_set_time(f.ctx, physicalTime));
 					// one GPU: CUDA-graph replay of whole steps; z-slabs: the slab stepper (halo exchange overlapped with interior work, dt
 					// MAX-reduced on the device) -- both keep dt and the physical time on the device
-					int rc = slab ? xf_slab_run(slab, f.d_U, f.d_U1, f.d_LU, Ss.nStepmax - Iteration, target_t, &done, &physicalTime, &err)
-								  : xf_run(f.ctx, f.d_U, f.d_U1, f.d_LU, f.BCs, Ss.nStepmax - Iteration, target_t, &done, &physicalTime, &err);
+					int rc = slab ? xf_slab_run(slab, f.d_U, f.d_U1, f.d_LU, nrun, target_t, &done, &physicalTime, &err)
+								  : xf_run(f.ctx, f.d_U, f.d_U1, f.d_LU, f.BCs, nrun, target_t, &done, &physicalTime, &err);
 					if (rc != XF_OK && rc != XF_ERR_NUMERIC)
 						throw std::runtime_error(std::string("fused time loop failed: ") + (slab ? xf_slab_last_error() : xf_last_error()));
 					Iteration += done;
@@ -182,11 +199,18 @@ namespace xfh
 					if (verbose && rank == 0)
 						std::cout << "N=" << std::setw(7) << Iteration << "  last dt: " << std::setw(14) << std::setprecision(8) << dt
 								  << "  End physicalTime: " << std::setw(14) << physicalTime << "\n";
+					if (error_out || done == 0)
+						break;
 				}
 			}
 			else
 				while (physicalTime < target_t)
 				{
+					if (out && ((Iteration % OutInterval == 0) || TimeLoopOut) && OutNum <= nOutput)
+					{
+						OutNum++, TimeLoopOut = false;
+						out->output(OutAtThis.spec, physicalTime, std::to_string(Iteration));
+					}
 					Iteration++;
 					dt = ComputeTimeStep();
 					if (physicalTime + dt > target_t)
@@ -202,9 +226,12 @@ namespace xfh
 				}
 			if (error_out || Ss.nStepmax <= Iteration)
 				break;
+			TimeLoopOut = true;
 		}
 		XFCK(xf_synchronize(f.ctx));
 		loop_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+		if (out) // the last step's output (XFLUIDS.cpp:309)
+			out->output(Ss.OutTimeStamps.back().spec, physicalTime, std::to_string(Iteration));
 		return error_out;
 	}
 

@@ -37,6 +37,32 @@ namespace xfh
 		bool EstimateFluidNAN(int flag);            // Fluids.cpp:963-1040
 	};
 
+	class XFLUIDS;
+	struct OutFmt;
+	struct OutVar;
+	// field output in the reference's file formats (xfh_output.cpp; XFLUIDS::Output & co, src/XFLUIDS.cpp:726-1793)
+	class FieldOutput
+	{
+	public:
+		struct Host;
+		explicit FieldOutput(XFLUIDS &x);
+		~FieldOutput();
+		// XFLUIDS::Output: `spec` = the "{-C=..;-P=..;-V=..}" part of the output stamp in charge, `step` = the iteration label
+		void output(const std::string &spec, double time, const std::string &step);
+		int OutDAT = 1, OutVTI = 0;
+		std::string dir, prefix;
+
+	private:
+		XFLUIDS &X;
+		Setup &S;
+		Host *h;
+		int nb[3], mn[3], mxi[3]; // OutSize VTI (XFLUIDS.cpp:35-62)
+		void copy_from_device();
+		std::vector<OutVar> variables() const;
+		void write_vti(const OutFmt &f, const std::vector<OutVar> &vars, const std::string &step, double time, bool compressed);
+		void write_cplt(const std::string &step, double time);
+	};
+
 	class XFLUIDS
 	{
 	public:
@@ -46,6 +72,8 @@ namespace xfh
 		std::vector<std::unique_ptr<Fluid>> fluids;
 		bool verbose = true;
 		double loop_seconds = 0;
+		std::unique_ptr<FieldOutput> out; // set by EnableOutput(): field files at the output stamps and at the end, like XFLUIDS::Evolution
+		void EnableOutput();
 
 		XFLUIDS(Setup &setup, int device);
 		~XFLUIDS();

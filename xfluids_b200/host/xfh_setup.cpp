@@ -63,6 +63,7 @@ namespace xfh
 
 		OutputDir = run.value("OutputDir", "output");
 		nStepmax = int(run.value("nStepMax", 10.0));
+		nStepmax_json = nStepmax;
 		RcalInterval = int(run.value("RcalInterval", 100.0));
 		RSources = eq.value("Sources_React", false);
 		PositivityPreserving = eq.value("PositivityPreserving", false);
@@ -166,6 +167,8 @@ namespace xfh
 		if (!match("-fp").empty()) fp_mode = std::atoi(match("-fp")[0].c_str());
 		if (!match("-pp").empty()) PositivityPreserving = std::atoi(match("-pp")[0].c_str()) != 0;
 		if (!match("-cfl").empty()) bl.CFLnumber = std::atof(match("-cfl")[0].c_str());
+		if (!match("-dv").empty()) select_dv = match("-dv")[0];
+		if (!match("-outdir").empty()) OutputDir = match("-outdir")[0];
 		if (!match("-visc").empty()) Visc = Visc_Heat = Visc_Diffu = std::atoi(match("-visc")[0].c_str()) != 0;
 		if (!match("-visc-heat").empty()) Visc_Heat = std::atoi(match("-visc-heat")[0].c_str()) != 0;
 		if (!match("-visc-diffu").empty()) Visc_Diffu = std::atoi(match("-visc-diffu")[0].c_str()) != 0;

@@ -47,7 +47,8 @@ namespace xfh
 
 		// ---- run (read_json.cpp:33-52)
 		std::string OutputDir = "output";
-		int nStepmax = 10;
+		std::string select_dv = "b200"; // SelectDv of the reference's build (part of every output file name, XFLUIDS.cpp:19); -dv= overrides
+		int nStepmax = 10, nStepmax_json = 10;
 		std::vector<OutStamp> OutTimeStamps;
 		bool write_checkpoint = false;
 		int RcalInterval = 100;
