@@ -235,6 +235,9 @@ int xf_profile_step(xf_ctx *ctx, double *d_U, double *d_U1, double *d_LU, const 
 /* roofline denominators measured on `device`: FP64 FMA rate (TFLOP/s, FMA = 2 flop), copy bandwidth (GB/s, read+write) */
 int xf_measure_peaks(int device, double *dfma_tflops, double *copy_gbs);
 
+/* FP64 issue rates of `device`, 1e12 thread-instructions per second: [0] DADD [1] DMUL [2] DFMA -- the strict (no-FMA) build issues DADD /
+ * DMUL where a contracted build issues DFMA, so its ceiling is an ISSUE rate, not a flop rate */
+int xf_measure_fp64_issue(int device, double tinst[3]);
 /* copy rates of this context's link for `bytes` of pinned host memory (GB/s each way, nothing else running): the e2e leg's denominators.
  * NOTE: the d2h pass overwrites the host buffer with the staging buffer's content -- call it on a scratch / about-to-be-refilled buffer. */
 int xf_measure_pcie(xf_ctx *ctx, void *h_pinned, size_t bytes, double *h2d_gbs, double *d2h_gbs);

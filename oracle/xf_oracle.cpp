@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 #define XO_MAXS 16 // upper bound for NUM_SPECIES / Emax-4 in fixed-size scratch arrays
 #define XO_MAXE (XO_MAXS + 4)
@@ -36,6 +37,10 @@ extern "C"
 		double dx, dy, dz, _dx, _dy, _dz, CFL, ncop_gamma;
 		int bc[6];
 		const double *Hia, *Hib, *Ri, *_Wi; // NASA-9 tables Hia[n*21+m*3+range], Hib[n*6+m*3+range]; Ri=Ru/Wi; _Wi=1/Wi
+		// viscous / heat-conduction / species-diffusion terms (Visc, Visc_Heat, Visc_Diffu; cmake/init_options.cmake:81-92)
+		int visc, visc_heat, visc_diffu;
+		double Yil_limiter, Dim_limiter, dim_max0; // Block limiters (iniset.cpp:358-359); Dim_max before scaling (0: single-process build)
+		const double *fit_visc, *fit_therm, *fit_Dkj, *Wi; // Setup::GetFitCoefficient results [NS*4], [NS*4], [NS*NS*4]; Wi kg/mol
 	} xo_cfg;
 
 	// every array of one fluid, reference names (Fluids.cpp:299-339, global_setup.h FlowData)
@@ -47,6 +52,8 @@ extern "C"
 		double *rho, *p, *u, *v, *w, *c, *gamma, *e, *H, *T, *y, *Ri, *Cp;
 		double uvw_c_max[6];
 		int error_flags[4]; // [0] rho/yi NaN guard, [1] primitive guard, [2] U/LU NaN guard, [3] unused
+		// viscous work arrays (FlowData: Vde[9], viscosity_aver, thermal_conduct_aver, Dkm_aver[N*NS], hi[N*NS])
+		double *Vde[9], *va, *tca, *Dkm, *hi;
 	} xo_state;
 }
 
@@ -908,6 +915,285 @@ static void UpdateFluidLU(const xo_cfg &c, xo_state &s)
 }
 
 // ---- ConVenction_block.hpp:10-617 GetLU, inviscid branch ----------------------------------------
+// ---- viscous block of GetLU (FDM_Method/ConVenction_block.hpp:424-575) ------------------------------------------------------------
+// viscosity/Fourth_Order/Visc_Order_kernels.hpp:16-74: velocity derivatives at the cells [B-2, B+inner+2) of every active direction
+static void GetCellCenterDerivative(const xo_cfg &c, xo_state &s)
+{
+	const double _twle = 1.0 / 12.0;
+	const double tX = c.DimX, tY = c.DimY, tZ = c.DimZ;
+	const size_t sx = 1, sy = c.Xmax, sz = size_t(c.Xmax) * c.Ymax;
+	const int i0 = c.DimX ? c.Bw_X - 2 : 0, i1 = c.DimX ? c.Bw_X + c.X_inner + 2 : 1;
+	const int j0 = c.DimY ? c.Bw_Y - 2 : 0, j1 = c.DimY ? c.Bw_Y + c.Y_inner + 2 : 1;
+	const int k0 = c.DimZ ? c.Bw_Z - 2 : 0, k1 = c.DimZ ? c.Bw_Z + c.Z_inner + 2 : 1;
+	for (int k = k0; k < k1; k++)
+		for (int j = j0; j < j1; j++)
+			for (int i = i0; i < i1; i++)
+			{
+				const size_t id = sz * k + sy * j + i;
+				auto D = [&](const double *q, size_t st, double _dl) { return (8.0 * (q[id + st] - q[id - st]) - (q[id + 2 * st] - q[id - 2 * st])) * _dl * _twle; };
+				double d[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // inactive directions: the reference multiplies out-of-range reads by DimX_t = 0
+				if (c.DimX)
+					d[0] = D(s.u, sx, c._dx) * tX, d[1] = D(s.v, sx, c._dx) * tX * tY, d[2] = D(s.w, sx, c._dx) * tX * tZ;
+				if (c.DimY)
+					d[3] = D(s.u, sy, c._dy) * tY * tX, d[4] = D(s.v, sy, c._dy) * tY, d[5] = D(s.w, sy, c._dy) * tY * tZ;
+				if (c.DimZ)
+					d[6] = D(s.u, sz, c._dz) * tZ * tX, d[7] = D(s.v, sz, c._dz) * tZ * tY, d[8] = D(s.w, sz, c._dz) * tZ;
+				for (int m = 0; m < 9; m++)
+					s.Vde[m][id] = d[m];
+			}
+}
+// viscosity/Visc_kernels.hpp:7-217: ghost fill of the four derivatives a direction's wall flux reads
+static void CenterDerivativeBC(const xo_cfg &c, xo_state &s, int dir)
+{
+	static const int sel[3][4] = {{3, 6, 4, 8}, {1, 7, 0, 8}, {2, 5, 0, 4}};
+	const int Bw = dir == 0 ? c.Bw_X : (dir == 1 ? c.Bw_Y : c.Bw_Z), inner = dir == 0 ? c.X_inner : (dir == 1 ? c.Y_inner : c.Z_inner);
+	const int nmax = dir == 0 ? c.Xmax : (dir == 1 ? c.Ymax : c.Zmax);
+	const size_t sy = c.Xmax, sz = size_t(c.Xmax) * c.Ymax;
+	auto idx = [&](int i, int j, int k) { return sz * k + sy * j + i; };
+	for (int side = 0; side < 2; side++)
+	{
+		const int BC = c.bc[2 * dir + side];
+		const int mirror_offset = side ? inner : 0, index_inner = side ? nmax - Bw - 1 : Bw, sign = side ? -1 : 1;
+		for (int k = 0; k < (dir == 2 ? Bw : c.Zmax); k++)
+			for (int j = 0; j < (dir == 1 ? Bw : c.Ymax); j++)
+				for (int i = 0; i < (dir == 0 ? Bw : c.Xmax); i++)
+				{
+					int ii = i, jj = j, kk = k;
+					int &g = dir == 0 ? ii : (dir == 1 ? jj : kk);
+					if (side)
+						g += nmax - Bw;
+					const size_t id = idx(ii, jj, kk);
+					auto at = [&](int t) { return dir == 0 ? idx(t, jj, kk) : (dir == 1 ? idx(ii, t, kk) : idx(ii, jj, t)); };
+					size_t src;
+					double sg = 1.0;
+					switch (BC)
+					{
+					case 2: src = at(2 * (Bw + mirror_offset) - 1 - g); break;
+					case 3: src = at(g + sign * inner); break;
+					case 1: src = at(index_inner); break;
+					case 4:
+						if (dir == 2)
+							continue; // the reference's mirror index (k - offset) is out of range (Visc_kernels.hpp:197): not reproduced
+						src = at(2 * (Bw + mirror_offset) - 1 - g), sg = -1.0;
+						break;
+					case 0:
+						for (int n = 0; n < 4; n++)
+							s.Vde[sel[dir][n]][id] = 0.0;
+						continue;
+					default: continue;
+					}
+					for (int n = 0; n < 4; n++)
+						s.Vde[sel[dir][n]][id] = sg < 0 ? -s.Vde[sel[dir][n]][src] : s.Vde[sel[dir][n]][src];
+				}
+	}
+}
+// Visc_device.h:10-101
+static inline double FitValue(const double *f, const double T)
+{
+	double v = f[3];
+	for (int i = 2; i >= 0; i--)
+		v = v * XO_LOG(T) + f[i];
+	return std::exp(v);
+}
+// Gettransport_coeff_aver (Visc_kernels.hpp:219-241) + Get_transport_coeff_aver (Visc_device.h:107-177), all cells
+static void GetTransportCoeff(const xo_cfg &c, xo_state &s)
+{
+	const int NS = c.NS;
+	const size_t N = size_t(c.Xmax) * c.Ymax * c.Zmax;
+	std::vector<double> X(NS);
+	for (size_t id = 0; id < N; id++)
+	{
+		const double T = s.T[id], p = s.p[id], rho = s.rho[id];
+		if (c.visc_diffu)
+			for (int ii = 0; ii < NS; ii++)
+				s.hi[ii + NS * id] = c.cop ? get_Enthalpy_NASA(c.Hia, c.Hib, T, c.Ri[ii], ii) : 0.0;
+		const double *yi = &s.y[NS * id];
+		double C_total = 0.0;
+		for (int i = 0; i < NS; i++)
+		{
+			X[i] = yi[i] * c._Wi[i] * 1e-3 * rho;
+			C_total = C_total + X[i];
+		}
+		const double _C_total = 1.0 / C_total;
+		for (int i = 0; i < NS; i++)
+			X[i] = X[i] * _C_total;
+		double va = 0.0, tca = 0.0;
+		for (int k = 0; k < NS; k++)
+		{
+			double denominator = 0.0;
+			for (int i = 0; i < NS; i++)
+			{ // PHI(specie[k], specie[i])
+				double phi = std::pow(c.Wi[i] / c.Wi[k], 0.25) * std::pow(FitValue(c.fit_visc + 4 * k, T) / FitValue(c.fit_visc + 4 * i, T), 0.5);
+				phi = (phi + 1.0) * (phi + 1.0) * 0.5 / std::sqrt(2.0);
+				phi = phi * std::pow(1.0 + c.Wi[k] / c.Wi[i], -0.5);
+				denominator = denominator + X[i] * phi;
+			}
+			const double _denominator = 1.0 / denominator;
+			va = va + X[k] * FitValue(c.fit_visc + 4 * k, T) * _denominator;
+			if (c.visc_heat)
+				tca = tca + X[k] * FitValue(c.fit_therm + 4 * k, T) * _denominator;
+		}
+		s.va[id] = va;
+		if (c.visc_heat)
+			s.tca[id] = tca;
+		if (c.visc_diffu)
+		{
+			double *Dk = &s.Dkm[NS * id];
+			if (NS > 1)
+				for (int k = 0; k < NS; k++)
+				{
+					double temp1 = 0.0, temp2 = 1.0e-20;
+					for (int i = 0; i < NS; i++)
+						if (i != k)
+						{
+							temp1 += (X[i] + 1.0e-40) * c.Wi[i];
+							temp2 += (X[i] + 1.0e-40) / (FitValue(c.fit_Dkj + 4 * (i * NS + k), T) / p + 1.0e-40);
+						}
+					if (!(0.0 < std::ceil(temp1))) // sycl::step(ceil(temp1), 0.0)
+						Dk[k] = FitValue(c.fit_Dkj + 4 * (k * NS + k), T) / p;
+					else
+						Dk[k] = temp1 / temp2 / rho * C_total;
+					Dk[k] *= 1.0e-1;
+				}
+			else
+			{
+				Dk[0] = FitValue(c.fit_Dkj, T) / p;
+				Dk[0] *= 1.0e-1;
+			}
+			for (int k = 0; k < NS; k++)
+				Dk[k] = (Dk[k] < 1.0e-10) ? 1.0e-10 : Dk[k];
+		}
+	}
+}
+// GetWallViscousFlux{X,Y,Z} (Visc_Order_kernels.hpp:76-340) with the macros of Fourth_Order/Flux_discrete.h
+static void GetWallViscousFlux(const xo_cfg &c, xo_state &s, int dir, double *Flux_wall, const double *Yil_limiter, const double *Diffu_limiter)
+{
+	const int NS = c.NS, E = c.Emax;
+	const double _sxtn = 1.0 / 16.0, _twfr = 1.0 / 24.0;
+	const double tX = c.DimX, tY = c.DimY, tZ = c.DimZ;
+	const size_t sy = c.Xmax, sz = size_t(c.Xmax) * c.Ymax, st = dir == 0 ? 1 : (dir == 1 ? sy : sz);
+	const double _dl = dir == 0 ? c._dx : (dir == 1 ? c._dy : c._dz);
+	const int i0 = c.Bw_X - (dir == 0), j0 = c.Bw_Y - (dir == 1), k0 = c.Bw_Z - (dir == 2);
+	for (int k = k0; k < c.Z_inner + c.Bw_Z; k++)
+		for (int j = j0; j < c.Y_inner + c.Bw_Y; j++)
+			for (int i = i0; i < c.X_inner + c.Bw_X; i++)
+			{
+				const size_t id = sz * k + sy * j + i, id_m1 = id - st, id_p1 = id + st, id_p2 = id + 2 * st;
+				auto avg = [&](const double *q) { return (9.0 * (q[id_p1] + q[id]) - (q[id_p2] + q[id_m1])) * _sxtn; };
+				const double *u = s.u, *v = s.v, *w = s.w;
+				std::vector<double> F_wall_v(E);
+				double f_x, f_y, f_z, u_hlf, v_hlf, w_hlf;
+				const double mue = avg(s.va);
+				const double lamada = -2.0 * _OT * mue;
+				if (dir == 0)
+				{
+					const double *Ducy = s.Vde[3], *Ducz = s.Vde[6], *Dvcy = s.Vde[4], *Dwcz = s.Vde[8];
+					f_x = (2.0 * mue + lamada) * (27.0 * (u[id_p1] - u[id]) - (u[id_p2] - u[id_m1])) * _dl * _twfr;
+					f_x += lamada * (9.0 * (Dvcy[id_p1] + Dvcy[id]) - (Dvcy[id_p2] + Dvcy[id_m1]) + 9.0 * (Dwcz[id_p1] + Dwcz[id]) - (Dwcz[id_p2] + Dwcz[id_m1])) * _sxtn;
+					f_y = mue * (27.0 * (v[id_p1] - v[id]) - (v[id_p2] - v[id_m1])) * _dl * _twfr * tY;
+					f_y += mue * (9.0 * (Ducy[id_p1] + Ducy[id]) - (Ducy[id_p2] + Ducy[id_m1])) * _sxtn * tY;
+					f_z = mue * (27.0 * (w[id_p1] - w[id]) - (w[id_p2] - w[id_m1])) * _dl * _twfr * tZ;
+					f_z += mue * (9.0 * (Ducz[id_p1] + Ducz[id]) - (Ducz[id_p2] + Ducz[id_m1])) * _sxtn * tZ;
+					u_hlf = avg(u), v_hlf = avg(v) * tY, w_hlf = avg(w) * tZ;
+				}
+				else if (dir == 1)
+				{
+					const double *Dvcx = s.Vde[1], *Dvcz = s.Vde[7], *Ducx = s.Vde[0], *Dwcz = s.Vde[8];
+					f_x = mue * (27.0 * (u[id_p1] - u[id]) - (u[id_p2] - u[id_m1])) * _dl * _twfr * tX;
+					f_x += mue * (9.0 * (Dvcx[id_p1] + Dvcx[id]) - (Dvcx[id_p2] + Dvcx[id_m1])) * _sxtn * tX;
+					f_y = (2.0 * mue + lamada) * (27.0 * (v[id_p1] - v[id]) - (v[id_p2] - v[id_m1])) * _dl * _twfr;
+					f_y += lamada * (9.0 * (Ducx[id_p1] + Ducx[id]) - (Ducx[id_p2] + Ducx[id_m1]) + 9.0 * (Dwcz[id_p1] + Dwcz[id]) - (Dwcz[id_p2] + Dwcz[id_m1])) * _sxtn;
+					f_z = mue * (27.0 * (w[id_p1] - w[id]) - (w[id_p2] - w[id_m1])) * _dl * _twfr * tZ;
+					f_z += mue * (9.0 * (Dvcz[id_p1] + Dvcz[id]) - (Dvcz[id_p2] + Dvcz[id_m1])) * _sxtn * tZ;
+					u_hlf = avg(u) * tX, v_hlf = avg(v), w_hlf = avg(w) * tZ;
+				}
+				else
+				{
+					const double *Dwcx = s.Vde[2], *Dwcy = s.Vde[5], *Ducx = s.Vde[0], *Dvcy = s.Vde[4];
+					f_x = mue * (27.0 * (u[id_p1] - u[id]) - (u[id_p2] - u[id_m1])) * _dl * _twfr * tX;
+					f_x += mue * (9.0 * (Dwcx[id_p1] + Dwcx[id]) - (Dwcx[id_p2] + Dwcx[id_m1])) * _sxtn * tX;
+					f_y = mue * (27.0 * (v[id_p1] - v[id]) - (v[id_p2] - v[id_m1])) * _dl * _twfr * tY;
+					f_y += mue * (9.0 * (Dwcy[id_p1] + Dwcy[id]) - (Dwcy[id_p2] + Dwcy[id_m1])) * _sxtn * tY;
+					f_z = (2.0 * mue + lamada) * (27.0 * (w[id_p1] - w[id]) - (w[id_p2] - w[id_m1])) * _dl * _twfr;
+					f_z += lamada * (9.0 * (Ducx[id_p1] + Ducx[id]) - (Ducx[id_p2] + Ducx[id_m1]) + 9.0 * (Dvcy[id_p1] + Dvcy[id]) - (Dvcy[id_p2] + Dvcy[id_m1])) * _sxtn;
+					u_hlf = avg(u) * tX, v_hlf = avg(v) * tY, w_hlf = avg(w);
+				}
+				F_wall_v[0] = 0.0, F_wall_v[1] = f_x, F_wall_v[2] = f_y, F_wall_v[3] = f_z;
+				F_wall_v[4] = f_x * u_hlf + f_y * v_hlf + f_z * w_hlf;
+				if (c.visc_heat)
+				{
+					double kk = avg(s.tca);
+					kk *= (27.0 * (s.T[id_p1] - s.T[id]) - (s.T[id_p2] - s.T[id_m1])) * _dl * _twfr;
+					F_wall_v[4] += kk;
+				}
+				if (c.visc_diffu)
+				{
+					const double rho_wall = avg(s.rho);
+					double CorrectTerm = 0.0, Dim_Yil = 1.0E-20;
+					std::vector<double> Yi_wall(NS, 0.0);
+					for (int l = 0; l < NS; l++)
+					{
+						const size_t g_p1 = l + NS * id_p1, g = l + NS * id, g_p2 = l + NS * id_p2, g_m1 = l + NS * id_m1;
+						const double hi_wall = (9.0 * (s.hi[g_p1] + s.hi[g]) - (s.hi[g_p2] + s.hi[g_m1])) * _sxtn;
+						const double Dim_wall = (9.0 * (s.Dkm[g_p1] + s.Dkm[g]) - (s.Dkm[g_p2] + s.Dkm[g_m1])) * _sxtn;
+						if (c.cop)
+						{
+							const double *Yi = s.y;
+							auto smin = [](double a, double b) { return (b < a) ? b : a; };
+							auto smax = [](double a, double b) { return (a < b) ? b : a; };
+							const double Yil_wall = smin(smax((27.0 * (Yi[g_p1] - Yi[g]) - (Yi[g_p2] - Yi[g_m1])) * _dl * _twfr, -Yil_limiter[l]), Yil_limiter[l]);
+							Yi_wall[l] = smin(smax((9.0 * (Yi[g_p1] + Yi[g]) - (Yi[g_p2] + Yi[g_m1])) * _sxtn, 1.0E-20), 1.0);
+							Dim_Yil = smin(smax(Dim_wall * Yil_wall, -Diffu_limiter[l]), Diffu_limiter[l]);
+							CorrectTerm += Dim_Yil;
+						}
+						F_wall_v[4] += rho_wall * hi_wall * Dim_Yil;
+					}
+					CorrectTerm *= rho_wall;
+					for (int p = 5; p < E; p++)
+						F_wall_v[p] = rho_wall * Dim_Yil - Yi_wall[p - 5] * CorrectTerm;
+				}
+				else
+					for (int p = 5; p < E; p++)
+						F_wall_v[p] = 0.0;
+				for (int n = 0; n < E; n++)
+					Flux_wall[n + E * id] -= F_wall_v[n];
+			}
+}
+static void ViscousBlock(const xo_cfg &c, xo_state &s)
+{
+	GetCellCenterDerivative(c, s);
+	for (int dir = 0; dir < 3; dir++)
+		if (dir == 0 ? c.DimX : (dir == 1 ? c.DimY : c.DimZ))
+			CenterDerivativeBC(c, s, dir);
+	GetTransportCoeff(c, s);
+	std::vector<double> yi_max(c.NS, 0.0), Dim_max(c.NS, 0.0);
+	if (c.visc_diffu)
+		for (int nn = 0; nn < c.NS; nn++)
+		{ // ConVenction_block.hpp:458-504: both reductions start from 0.0
+			double ymin = 0.0, ymax = 0.0;
+			for (int k = c.Bw_Z; k < c.Zmax - c.Bw_Z; k++)
+				for (int j = c.Bw_Y; j < c.Ymax - c.Bw_Y; j++)
+					for (int i = c.Bw_X; i < c.Xmax - c.Bw_X; i++)
+					{
+						const double y = s.y[c.NS * (size_t(c.Xmax) * c.Ymax * k + size_t(c.Xmax) * j + i) + nn];
+						ymin = (y < ymin) ? y : ymin, ymax = (ymax < y) ? y : ymax;
+					}
+			double dmax = c.dim_max0;
+			if (c.dim_max0 != 0.0)
+				ymin = (ymin < 0.0) ? 0.0 : ymin, ymax = (1.0 < ymax) ? 1.0 : ymax;
+			ymax -= ymin;
+			ymax *= c.Yil_limiter;
+			dmax *= c.Dim_limiter * ymax;
+			yi_max[nn] = ymax, Dim_max[nn] = dmax;
+		}
+	if (c.DimX)
+		GetWallViscousFlux(c, s, 0, s.FluxFw, yi_max.data(), Dim_max.data());
+	if (c.DimY)
+		GetWallViscousFlux(c, s, 1, s.FluxGw, yi_max.data(), Dim_max.data());
+	if (c.DimZ)
+		GetWallViscousFlux(c, s, 2, s.FluxHw, yi_max.data(), Dim_max.data());
+}
+
 static void GetLU(const xo_cfg &c, xo_state &s, const double *UI)
 {
 	if (c.DimX)
@@ -938,6 +1224,8 @@ static void GetLU(const xo_cfg &c, xo_state &s, const double *UI)
 		if (c.DimZ)
 			PositivityPreserving(c, 2, UI, s.FluxH, s.FluxHw, lz0, c.CFL / lz0);
 	}
+	if (c.visc)
+		ViscousBlock(c, s);
 	UpdateFluidLU(c, s);
 }
 
@@ -1106,6 +1394,12 @@ extern "C"
 		s->eigen_block_x = A(E), s->eigen_block_y = A(E), s->eigen_block_z = A(E);
 		s->rho = A(N), s->p = A(N), s->u = A(N), s->v = A(N), s->w = A(N), s->c = A(N), s->gamma = A(N);
 		s->e = A(N), s->H = A(N), s->T = A(N), s->Ri = A(N), s->Cp = A(N), s->y = A(N * NS);
+		if (c->visc)
+		{
+			for (int m = 0; m < 9; m++)
+				s->Vde[m] = A(N);
+			s->va = A(N), s->tca = A(N), s->Dkm = A(N * NS), s->hi = A(N * NS);
+		}
 		return s;
 	}
 	void xo_state_destroy(xo_state *s)
@@ -1114,6 +1408,9 @@ extern "C"
 						s->eigen_block_x, s->eigen_block_y, s->eigen_block_z, s->rho, s->p, s->u, s->v, s->w, s->c, s->gamma, s->e, s->H, s->T, s->Ri, s->Cp, s->y};
 		for (double *p : ps)
 			std::free(p);
+		for (int m = 0; m < 9; m++)
+			std::free(s->Vde[m]);
+		std::free(s->va), std::free(s->tca), std::free(s->Dkm), std::free(s->hi);
 		std::free(s);
 	}
 	// named array access: returns pointer, *len = number of doubles
@@ -1125,7 +1422,9 @@ extern "C"
 			const char *n;
 			double *p;
 			size_t l;
-		} t[] = {{"U", s->U, N * E}, {"U1", s->U1, N * E}, {"LU", s->LU, N * E}, {"FluxF", s->FluxF, N * E}, {"FluxG", s->FluxG, N * E}, {"FluxH", s->FluxH, N * E}, {"FluxFw", s->FluxFw, N * E}, {"FluxGw", s->FluxGw, N * E}, {"FluxHw", s->FluxHw, N * E}, {"rho", s->rho, N}, {"p", s->p, N}, {"u", s->u, N}, {"v", s->v, N}, {"w", s->w, N}, {"c", s->c, N}, {"gamma", s->gamma, N}, {"e", s->e, N}, {"H", s->H, N}, {"T", s->T, N}, {"R", s->Ri, N}, {"Cp", s->Cp, N}, {"y", s->y, N * NS}, {"eigen_block_x", s->eigen_block_x, E}, {"eigen_block_y", s->eigen_block_y, E}, {"eigen_block_z", s->eigen_block_z, E}, {"uvw_c_max", s->uvw_c_max, 6}};
+		} t[] = {{"U", s->U, N * E}, {"U1", s->U1, N * E}, {"LU", s->LU, N * E}, {"FluxF", s->FluxF, N * E}, {"FluxG", s->FluxG, N * E}, {"FluxH", s->FluxH, N * E}, {"FluxFw", s->FluxFw, N * E}, {"FluxGw", s->FluxGw, N * E}, {"FluxHw", s->FluxHw, N * E}, {"rho", s->rho, N}, {"p", s->p, N}, {"u", s->u, N}, {"v", s->v, N}, {"w", s->w, N}, {"c", s->c, N}, {"gamma", s->gamma, N}, {"e", s->e, N}, {"H", s->H, N}, {"T", s->T, N}, {"R", s->Ri, N}, {"Cp", s->Cp, N}, {"y", s->y, N * NS}, {"eigen_block_x", s->eigen_block_x, E}, {"eigen_block_y", s->eigen_block_y, E}, {"eigen_block_z", s->eigen_block_z, E}, {"uvw_c_max", s->uvw_c_max, 6},
+				 {"visc", s->va, N}, {"therm", s->tca, N}, {"Dkm", s->Dkm, N * NS}, {"hi", s->hi, N * NS}, {"Vde0", s->Vde[0], N}, {"Vde1", s->Vde[1], N}, {"Vde2", s->Vde[2], N},
+				 {"Vde3", s->Vde[3], N}, {"Vde4", s->Vde[4], N}, {"Vde5", s->Vde[5], N}, {"Vde6", s->Vde[6], N}, {"Vde7", s->Vde[7], N}, {"Vde8", s->Vde[8], N}};
 		for (auto &e : t)
 			if (!std::strcmp(e.n, name))
 			{

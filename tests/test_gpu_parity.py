@@ -379,3 +379,41 @@ def test_ragged_sizes_and_scheme_matrix_vs_oracle(case, res, weno, alpha, pp):
         errs.append(xfgpu.rel_linf(U, o.arr("U"), E))
         assert np.array_equal(U, o.arr("U")), errs
     print("\n%s %s weno%d alpha=%d pp=%d: bit-exact (all cells) after 1 and 5 steps" % (case, res, weno, alpha, pp))
+
+
+# ---- the opt-in TMA-fed marching sweeps (XF_MARCH=1, csrc/xf_march.cuh): fused divergence / update, bit-identical to the default path ----
+@pytest.mark.parametrize("case,weno,pp", [("sbi", 5, 0), ("sbi", 6, 1), ("jet", 5, 0), ("shock-tube", 7, 0), ("vortex", 5, 0), ("sbi", 7, 0)])
+def test_marching_sweeps_equal_reference_golden_bitwise(monkeypatch, case, weno, pp):
+    import xfgpu
+    monkeypatch.setenv("XF_MARCH", "1")
+    g, res = golden_next(case, weno, pp) if (pp or weno == 6) else golden(case, weno)
+    eng = xfgpu.make_engine(case, res, weno=weno, pp=pp, cfl=float(g["cfl"]) if "cfl" in g else None)
+    eng.set_state(g["ic_U"], g["ic_T"])
+    eng.boundary(eng.U, eng.bc)
+    assert eng.update_states(eng.U) == 0
+    done, t, err = eng.run(eng.bc, 10)
+    assert (done, err) == (10, 0)
+    assert np.array_equal(eng.download(eng.U), g["U_step10"])
+    eng.close()
+
+
+def test_marching_sweeps_segmented_2d_equal_tiled_bitwise(monkeypatch):
+    """A 2-D block with few columns: the march is cut into segments along y, and stage 2 (which updates its own input) falls back to
+    accumulate + update kernel.  Same bits as the tiled default over 6 steps."""
+    import xfgpu
+    from xfluids_b200 import host
+    res = (48, 700, 0)
+    s = host.Setup(os.path.join(xfref.REPO, "settings", "2d-riemann.json"), ["-run=%d,%d,%d" % res])
+    U0, T0 = s.initial_condition()
+    outs = []
+    for march in ("0", "1"):
+        monkeypatch.setenv("XF_MARCH", march)
+        eng = xfgpu.make_engine("riemann", res, weno=5)
+        eng.set_state(U0, T0)
+        eng.boundary(eng.U, eng.bc)
+        assert eng.update_states(eng.U) == 0
+        done, t, err = eng.run(eng.bc, 6)
+        assert (done, err) == (6, 0)
+        outs.append(eng.download(eng.U))
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])

@@ -78,3 +78,48 @@ def test_oracle_matches_reference_golden_cu6_and_positivity(case, weno, pp):
     assert np.array_equal(o.arr("U"), g["U_step10"])
     assert np.array_equal(o.arr("T"), g["T_step10"])
     assert not o.flags().any()
+
+
+VISC_FIXTURES = ["sbi_w5_visc", "jet_w5_visc", "sbi_w6_glf_pp_visc"]
+
+
+@pytest.mark.parametrize("name", VISC_FIXTURES)
+def test_oracle_viscous_block_matches_reference_golden(name):
+    """the viscous / heat-conduction / species-diffusion block of GetLU (ConVenction_block.hpp:424-575) restated in the
+    oracle against the UNMODIFIED reference built with Visc, Visc_Heat and Visc_Diffu (tests/golden/make_golden_visc.py).  The oracle
+    runs on this host's glibc like the reference did, so every intermediate and the state after 10 steps are bit-exact."""
+    from xfluids_b200 import host
+    g = np.load(os.path.join(xfref.GOLDEN, name + ".npz"))
+    case = name.split("_")[0]
+    res = tuple(int(x) for x in g["res"])
+    weno, alpha, pp, cfl = int(g["weno"]), int(g["alpha"]), int(g["pp"]), float(g["cfl"])
+    js = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json"}[case]
+    s = host.Setup(os.path.join(xfref.REPO, "settings", js), ["-run=%d,%d,%d" % res, "-visc=1"])
+    assert np.array_equal(np.ctypeslib.as_array(s.transport.fit_visc, shape=(s.num_species * 4,)), g["fit_visc"])
+    o = xfref.Oracle(case, res, weno=weno, alpha=alpha, pp=pp, cfl=cfl, transport=s.transport)
+    o.set_state(g["ic_U"], g["ic_T"])
+    assert o.startup() == 0
+    assert o.get_dt() == g["dt"][0]
+    o.boundary(0); o.update_states(0); o.get_lu(0)
+    c = o.cfg
+    wide = np.zeros((c.Zmax, c.Ymax, c.Xmax), bool)
+    wide[c.Bw_Z - 2:c.Zmax - c.Bw_Z + 2, c.Bw_Y - 2:c.Ymax - c.Bw_Y + 2, c.Bw_X - 2:c.Xmax - c.Bw_X + 2] = True
+    wide = wide.ravel()
+    for m in range(9):
+        assert np.array_equal(o.arr("Vde%d" % m)[wide], g["s1_Vde%d" % m][wide]), "Vde%d" % m
+    for k in ("visc", "therm", "Dkm", "hi"):
+        assert np.array_equal(o.arr(k), g["s1_" + k]), k
+    for k, a in (("Fwx", "FluxFw"), ("Fwy", "FluxGw"), ("Fwz", "FluxHw")):
+        assert np.array_equal(o.arr(a), g["s1_" + k]), k
+    assert np.array_equal(o.arr("LU"), g["s1_LU"])
+    # the viscous terms are not a rounding-level effect in these fixtures: the inviscid oracle gives another LU
+    o2 = xfref.Oracle(case, res, weno=weno, alpha=alpha, pp=pp, cfl=cfl)
+    o2.set_state(g["ic_U"], g["ic_T"]); o2.startup(); o2.boundary(0); o2.update_states(0); o2.get_lu(0)
+    assert not np.array_equal(o2.arr("LU"), g["s1_LU"])
+    o.set_state(g["ic_U"], g["ic_T"])
+    o.startup()
+    n, dts, t = o.run(10)
+    assert n == 10 and np.array_equal(np.array(dts), g["dt"][:10])
+    assert np.array_equal(o.arr("U"), g["U_step10"])
+    assert np.array_equal(o.arr("T"), g["T_step10"])
+    assert not o.flags().any()

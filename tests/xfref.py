@@ -22,7 +22,9 @@ class XoCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("Xmax", "Ymax", "Zmax", "X_inner", "Y_inner", "Z_inner", "Bw_X", "Bw_Y", "Bw_Z",
                                        "DimX", "DimY", "DimZ", "NS", "Emax", "NCOP", "cop", "ghost_species", "weno", "alpha", "positivity")] + \
                [(n, C.c_double) for n in ("dx", "dy", "dz", "_dx", "_dy", "_dz", "CFL", "ncop_gamma")] + \
-               [("bc", C.c_int * 6)] + [(n, C.POINTER(C.c_double)) for n in ("Hia", "Hib", "Ri", "_Wi")]
+               [("bc", C.c_int * 6)] + [(n, C.POINTER(C.c_double)) for n in ("Hia", "Hib", "Ri", "_Wi")] + \
+               [(n, C.c_int) for n in ("visc", "visc_heat", "visc_diffu")] + [(n, C.c_double) for n in ("Yil_limiter", "Dim_limiter", "dim_max0")] + \
+               [(n, C.POINTER(C.c_double)) for n in ("fit_visc", "fit_therm", "fit_Dkj", "Wi_kg")]
 
 
 # ---- case table: what cmake/init_sample.cmake + the north_star overrides select
@@ -69,7 +71,8 @@ def read_thermal(names):
 class Oracle:
     """One oracle state (all reference arrays, AoS) for one case/grid."""
 
-    def __init__(self, case, res, weno=5, alpha=2, so=ORACLE_SO, pp=0, cfl=None):
+    def __init__(self, case, res, weno=5, alpha=2, so=ORACLE_SO, pp=0, cfl=None, transport=None):
+        """transport: a host.Setup.transport (XfTransport) to switch the viscous block on (fits and limiters are the host Setup's)."""
         if not os.path.exists(so):
             subprocess.check_call([os.path.join(REPO, "oracle", "build_oracle.sh")])
         self.lib = L = C.CDLL(so)
@@ -99,6 +102,11 @@ class Oracle:
             cfg.CFL = cfl
         for n in ("Hia", "Hib", "Ri", "_Wi"):
             setattr(cfg, n, getattr(self, n).ctypes.data_as(C.POINTER(C.c_double)))
+        if transport is not None and transport.visc:
+            self._tr = transport
+            cfg.visc, cfg.visc_heat, cfg.visc_diffu = transport.visc, transport.visc_heat, transport.visc_diffu
+            cfg.Yil_limiter, cfg.Dim_limiter, cfg.dim_max0 = transport.Yil_limiter, transport.Dim_limiter, transport.dim_max0
+            cfg.fit_visc, cfg.fit_therm, cfg.fit_Dkj, cfg.Wi_kg = transport.fit_visc, transport.fit_therm, transport.fit_Dkj, transport.Wi
         self.st = L.xo_state_create(C.byref(cfg))
         self.N = cfg.Xmax * cfg.Ymax * cfg.Zmax
 

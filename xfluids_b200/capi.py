@@ -96,6 +96,7 @@ _PROTOS = {
     "xf_measure_peaks": (C.c_int, [C.c_int, _DP, _DP]),
     "xf_log_eval": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
     "xf_measure_pcie": (C.c_int, [_P, _P, C.c_size_t, _DP, _DP]),
+    "xf_measure_fp64_issue": (C.c_int, [C.c_int, C.c_double * 3]),
     "xf_slab_last_error": (C.c_char_p, []),
     "xf_comm_unique_id": (C.c_int, [C.c_char * 128]),
     "xf_comm_create": (C.c_int, [C.c_char * 128, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -159,6 +160,14 @@ def measure_peaks(device=0):
     a, b = C.c_double(), C.c_double()
     L.check(L.dll.xf_measure_peaks(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def measure_fp64_issue(device=0):
+    """(DADD, DMUL, DFMA) issue rates in 1e12 thread-instructions per second."""
+    L = Lib.get()
+    v = (C.c_double * 3)()
+    L.check(L.dll.xf_measure_fp64_issue(device, v))
+    return tuple(v)
 
 
 def log_eval(x, device=0):

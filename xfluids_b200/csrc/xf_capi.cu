@@ -123,6 +123,28 @@ __global__ void __launch_bounds__(256) k_peak_dfma(double *out, int iters, doubl
 	if (r == 123.456)
 		out[0] = r;
 }
+// FP64 issue-rate probes: 8 independent chains of one opcode per thread (OP 0 DADD, 1 DMUL, 2 DFMA); strict builds issue DADD / DMUL where
+// a contracted build would issue DFMA, so the honest ceiling of the parity mode is the DADD / DMUL issue rate
+template <int OP>
+__global__ void __launch_bounds__(256) k_peak_op(double *out, int iters, double a, double b)
+{
+	double x[8];
+#pragma unroll
+	for (int q = 0; q < 8; q++)
+		x[q] = threadIdx.x * 1e-9 + q;
+	for (int i = 0; i < iters; i++)
+	{
+#pragma unroll
+		for (int q = 0; q < 8; q++)
+			x[q] = OP == 0 ? __dadd_rn(x[q], b) : (OP == 1 ? __dmul_rn(x[q], a) : fma(x[q], a, b));
+	}
+	double r = 0;
+#pragma unroll
+	for (int q = 0; q < 8; q++)
+		r += x[q];
+	if (r == 123.456)
+		out[0] = r;
+}
 __global__ void __launch_bounds__(256) k_peak_copy(const double2 *__restrict__ in, double2 *__restrict__ out, size_t n)
 {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1123,6 +1145,45 @@ extern "C"
 		}
 		cudaEventDestroy(a), cudaEventDestroy(b);
 		return rc;
+	}
+
+	// FP64 instruction issue rates of `device` in 1e12 thread-instructions per second: [0] DADD, [1] DMUL, [2] DFMA (best of 5 each)
+	int xf_measure_fp64_issue(int device, double tinst[3])
+	{
+		CU(cudaSetDevice(device));
+		cudaDeviceProp pr;
+		CU(cudaGetDeviceProperties(&pr, device));
+		cudaEvent_t a, b;
+		CU(cudaEventCreate(&a));
+		CU(cudaEventCreate(&b));
+		double *out = nullptr;
+		CU(cudaMalloc((void **)&out, 64));
+		const int iters = 1 << 14, blocks = pr.multiProcessorCount * 8;
+		for (int op = 0; op < 3; op++)
+		{
+			double best = 0;
+			for (int rep = 0; rep < 6; rep++)
+			{
+				CU(cudaEventRecord(a, 0));
+				if (op == 0)
+					k_peak_op<0><<<blocks, 256>>>(out, iters, 0.999999, 1e-7);
+				else if (op == 1)
+					k_peak_op<1><<<blocks, 256>>>(out, iters, 0.999999, 1e-7);
+				else
+					k_peak_op<2><<<blocks, 256>>>(out, iters, 0.999999, 1e-7);
+				CU(cudaEventRecord(b, 0));
+				CU(cudaEventSynchronize(b));
+				float ms;
+				CU(cudaEventElapsedTime(&ms, a, b));
+				const double t = 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+				if (rep && t > best)
+					best = t;
+			}
+			tinst[op] = best;
+		}
+		cudaFree(out);
+		cudaEventDestroy(a), cudaEventDestroy(b);
+		return XF_OK;
 	}
 
 	// ---- halo -----------------------------------------------------------------------------------
