@@ -417,3 +417,38 @@ def test_marching_sweeps_segmented_2d_equal_tiled_bitwise(monkeypatch):
         outs.append(eng.download(eng.U))
         eng.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+# ---- update -> recovery fusion (k_rk_prim + k_prim_shell; opt-in with XF_FUSE_PRIM=1: bit-identical, measured slower, profiles/r02_tuning.md) ----
+@pytest.mark.parametrize("case,weno,pp,alpha,nsteps", [("sbi", 5, 0, 2, 12), ("sbi", 6, 1, 3, 7), ("jet", 5, 0, 2, 5), ("vortex", 5, 0, 2, 20),
+                                                       ("riemann", 5, 0, 1, 5), ("shock-tube", 7, 0, 2, 9), ("sbi", 7, 0, 2, 2)])
+def test_update_recovery_fusion_equals_unfused_bitwise(monkeypatch, case, weno, pp, alpha, nsteps):
+    """The stage update that goes straight on to the next stage's primitive recovery (deep cells in k_rk_prim, the shell after the ghost
+    fill in k_prim_shell) against the separate kernels: U, the temperature field, the time and the error flags after runs that take the
+    single-step graph, the batch-opening, middle and closing graphs.  GhostSpecies cases (sbi) renormalise U inside the recovery, so a cell
+    recovered twice or before the ghost fill has read it would show here."""
+    import xfgpu
+    from xfluids_b200 import host
+    res = {"sbi": (40, 24, 24), "jet": (32, 20, 20), "vortex": (64, 48, 0), "riemann": (56, 40, 0), "shock-tube": (200, 0, 0)}[case]
+    js = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json", "vortex": "2d-euler-vortex.json", "riemann": "2d-riemann.json", "shock-tube": "1d-shock-tube.json"}[case]
+    U0, T0 = host.Setup(os.path.join(xfref.REPO, "settings", js), ["-run=%d,%d,%d" % res]).initial_condition()
+    outs = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("XF_FUSE_PRIM", fuse)
+        eng = xfgpu.make_engine(case, res, weno=weno, pp=pp, alpha=alpha, cfl=0.9 if pp else None)
+        eng.set_state(U0, T0)
+        eng.boundary(eng.U, eng.bc)
+        assert eng.update_states(eng.U) == 0
+        l0 = eng.launches()
+        done, t, err = eng.run(eng.bc, nsteps)
+        assert (done, err) == (nsteps, 0)
+        # a second call continues from the state the first one left (the deep cells must not be recovered twice)
+        done2, t2, err2 = eng.run(eng.bc, 3)
+        assert (done2, err2) == (3, 0)
+        outs.append((eng.download(eng.U), eng.get_scalar("T"), eng.get_scalar("p"), t2, eng.launches() - l0))
+        eng.close()
+    assert outs[0][3] == outs[1][3]
+    for q in range(3):
+        assert np.array_equal(outs[0][q], outs[1][q]), q
+    if case in ("sbi", "jet"):   # 3-D: the fused path launches k_prim_shell beside k_prim for the boundary planes
+        assert outs[0][4] != outs[1][4], "both runs launched the same kernels: the fused path did not run"

@@ -31,5 +31,8 @@ ncu --set full --clock-control none -k 'regex:k_visc_flux|k_transport|k_vde' -s 
 for r in sbi512 w7 riemann vortex visc; do python tools/ncu_summary.py full $O/r02_full_$r.ncu-rep > $O/r02_ncu_full_$r.md 2>/dev/null; done
 ncu -i $O/r02_full_sbi512.ncu-rep --page source --csv > $O/r02_full_sbi512_source.csv 2>/dev/null
 python tools/ncu_summary.py list $O/r02_launches_sbi512.csv > $O/r02_launches_sbi512.md 2>/dev/null
-rm -f $O/*.ncu-rep.tmp
+# gpurun brings back at most 64 MiB: keep the summaries, drop the raw reports, compress the source page
+gzip -9 -f $O/r02_full_sbi512_source.csv
+rm -f $O/*.ncu-rep.tmp $O/*.ncu-rep
+du -sh gpurun_out
 ls -la $O | head -60

@@ -53,16 +53,20 @@ struct XfTable
 	decltype(&xf_strict::launch_sweep_x) sweep_x;
 	decltype(&xf_strict::launch_march) march;
 	decltype(&xf_strict::launch_visc) visc;
+	decltype(&xf_strict::launch_prim_shell) prim_shell;
+	decltype(&xf_strict::launch_rk_prim) rk_prim;
 };
 static const XfTable T_STRICT = {xf_strict::launch_prim, xf_strict::launch_sweeps, xf_strict::launch_lu, xf_strict::launch_rk, xf_strict::launch_nan,
 								 xf_strict::launch_bc, xf_strict::launch_dt, xf_strict::launch_dt_final, xf_strict::launch_layout,
-								 xf_strict::launch_scalar_pad, xf_strict::launch_halo, xf_strict::launch_sweep_x, xf_strict::launch_march, xf_strict::launch_visc};
+								 xf_strict::launch_scalar_pad, xf_strict::launch_halo, xf_strict::launch_sweep_x, xf_strict::launch_march, xf_strict::launch_visc,
+								 xf_strict::launch_prim_shell, xf_strict::launch_rk_prim};
 // fast mode: FMA contraction in the sweeps / LU / RK only.  Primitive recovery stays strict: its Newton loop stops on an
 // absolute tolerance and is capped/limited, so a 1-ulp difference can change the trip count and move T by O(1e-6)
 // (measured: 2e-6 relative on U after one jet step with a contracted prim kernel).
 static const XfTable T_FAST = {xf_strict::launch_prim, xf_fast::launch_sweeps, xf_fast::launch_lu, xf_fast::launch_rk, xf_fast::launch_nan,
 							   xf_fast::launch_bc, xf_fast::launch_dt, xf_fast::launch_dt_final, xf_fast::launch_layout,
-							   xf_fast::launch_scalar_pad, xf_fast::launch_halo, xf_fast::launch_sweep_x, xf_fast::launch_march, xf_fast::launch_visc};
+							   xf_fast::launch_scalar_pad, xf_fast::launch_halo, xf_fast::launch_sweep_x, xf_fast::launch_march, xf_fast::launch_visc,
+							   nullptr, nullptr}; // no update -> recovery fusion in fast mode: the recovery must not be compiled with FMA contraction
 
 struct xf_ctx
 {
@@ -85,11 +89,24 @@ struct xf_ctx
 	long long launches = 0;
 	const double *lastUI = nullptr; // field of the last xf_update_states (its component 0 is rho)
 	// CUDA graph of one time step (xf_run)
-	cudaGraphExec_t gexec = nullptr;
+	// [0] a self-contained step; with the update -> recovery fusion also [2] the first step of a batch (leaves the deep cells of U
+	// recovered for the next step), [3] a middle step (finds them recovered and leaves them so), [1] the last step of a batch
+	cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};
 	const double *gU = nullptr, *gU1 = nullptr, *gLU = nullptr;
 	int gbc[6] = {-1, -1, -1, -1, -1, -1};
 	double gt_end = 0;
-	long long glaunches = 0; // kernel launches inside one replay
+	long long glaunches[4] = {0, 0, 0, 0}; // kernel launches inside one replay
+	// XF_FUSE_PRIM=1 (default 0): the stage update of stages 1 and 2 (and of stage 3 inside a batch of xf_run) goes straight on to the next
+	// stage's primitive recovery for the cells no ghost fill reads (k_rk_prim); strict mode with the tiled sweeps only.  Bit-identical, and
+	// measured SLOWER than the two kernels (SBI 512^3: 29.4 ms against 9.9 + 10.7 ms per stage, profiles/r02_tuning.md): at the 128
+	// registers the recovery needs, 16 warps per SM cannot keep the update's 73 loads per cell in flight
+	int fuse = 0;
+	void drop_graphs()
+	{
+		for (int i = 0; i < 4; i++)
+			if (gexec[i])
+				cudaGraphExecDestroy(gexec[i]), gexec[i] = nullptr;
+	}
 	// TMA tensor maps of the marching sweeps: per (sweep input field, direction); the primitive / Y maps are per direction
 	std::map<std::pair<const void *, int>, XfTma> tma;
 	// 1 (default): tiled y / z sweeps store the wall fluxes, one kernel forms the divergence and the stage update.  0 (XF_MARCH=1): the
@@ -243,6 +260,8 @@ extern "C"
 		const size_t N = (size_t)d.N;
 		const char *march = std::getenv("XF_MARCH");
 		c->tiled = (march && march[0] == '1') ? 0 : 1;
+		const char *fuse = std::getenv("XF_FUSE_PRIM");
+		c->fuse = (fuse && fuse[0] == '1') ? 1 : 0;
 		// every failure from here on goes through one exit that releases what has been allocated; the first failure wins
 		int rc = 0;
 		auto alloc = [&](double **p, size_t n)
@@ -299,8 +318,7 @@ extern "C"
 			return XF_OK;
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->stream);
-		if (c->gexec)
-			cudaGraphExecDestroy(c->gexec);
+		c->drop_graphs();
 		for (void *p : c->owned)
 			cudaFree(p);
 		if (c->stage)
@@ -319,8 +337,7 @@ extern "C"
 	int xf_set_stream(xf_ctx *c, void *s)
 	{
 		c->stream = (cudaStream_t)s;
-		if (c->gexec)
-			cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+		c->drop_graphs();
 		return XF_OK;
 	}
 	int xf_synchronize(xf_ctx *c)
@@ -468,6 +485,18 @@ extern "C"
 		return XF_OK;
 	}
 	static int update_states(xf_ctx *c, double *U, bool gather_dt) { return update_states_range(c, U, gather_dt, true, 0, c->d.Zmax); }
+	// ---- update -> recovery fusion (k_rk_prim / k_prim_shell) ----
+	static bool can_fuse(const xf_ctx *c) { return c->fuse && c->tiled && c->t->rk_prim != nullptr; }
+	static int prim_flags(const xf_ctx *c, bool gather_dt) { return (gather_dt ? 1 : 0) | ((c->sc.artificial_type == 3 && c->sc.weno_order != 7) ? 2 : 0); }
+	// the cells the previous stage's k_rk_prim left out: ghosts and the inner cells the ghost fill has just read.  The dt maxima were
+	// reset ahead of that kernel, the list of unconverged cells holds its entries.
+	static int update_states_shell(xf_ctx *c, double *U, bool gather_dt)
+	{
+		XF_DEVICE(c);
+		KL(c->t->prim_shell(c->d, c->th, c->ns, c->cop, U, prim_flags(c, gather_dt), c->stream, &c->launches));
+		c->lastUI = U;
+		return XF_OK;
+	}
 
 	// ---- wall-flux fields of the block-level API (FluxFw / Gw / Hw): allocated on first use, the fused path never stores wall fluxes ----
 	static int ensure_fw(xf_ctx *c)
@@ -479,8 +508,7 @@ extern "C"
 				int rc = dmalloc(c, &d.Fw[dir], (size_t)d.N * c->E);
 				if (rc)
 					return rc;
-				if (c->gexec) // XfDev travels by value inside captured launches
-					cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+				c->drop_graphs(); // XfDev travels by value inside captured launches
 			}
 		return 0;
 	}
@@ -497,8 +525,7 @@ extern "C"
 		std::memset(&v, 0, sizeof(v));
 		v.Vde = keep[0], v.va = keep[1], v.tca = keep[2], v.Dkm = keep[3], v.hi = keep[4], v.lim = keep_lim;
 		v.on = tr->visc ? 1 : 0, v.heat = (tr->visc && tr->visc_heat) ? 1 : 0, v.diffu = (tr->visc && tr->visc_diffu) ? 1 : 0;
-		if (c->gexec) // the parameter block travels by value inside captured launches
-			cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
+		c->drop_graphs(); // the parameter block travels by value inside captured launches
 		if (!v.on)
 			return XF_OK;
 		if (!c->tiled)
@@ -638,7 +665,8 @@ extern "C"
 	// sweep the cells (planes) [ka, kb) (absolute indices; < 0: all inner planes).  Every direction adds its part of the divergence to LU in
 	// the reference's x -> y -> z order (UpdateFluidLU, Reconstruction_kernels.hpp:201-234); with `finish` the last active direction goes on
 	// to the NaN guard and the stage update in the same kernel, and neither wall fluxes nor LU reach HBM.
-	static int stage_sweeps(xf_ctx *c, double *U, double *U1, double *LU, int flag, int dirmask, int kp0, int kp1, int ka, int kb, bool finish)
+	// nflags >= 0 (tiled sweeps, strict mode): the update goes on to the NEXT stage's primitive recovery of the deep cells with these gather flags
+	static int stage_sweeps(xf_ctx *c, double *U, double *U1, double *LU, int flag, int dirmask, int kp0, int kp1, int ka, int kb, bool finish, int nflags = -1)
 	{
 		XF_DEVICE(c);
 		const XfDev &d = c->d;
@@ -660,6 +688,13 @@ extern "C"
 				if (c->vs.on)
 				{ // viscous wall fluxes are subtracted once every direction's inviscid wall flux is in memory (ConVenction_block.hpp:424-575)
 					KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches));
+				}
+				if (nflags >= 0)
+				{
+					if (nflags & 1)
+						CU(cudaMemsetAsync(d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
+					KL(c->t->rk_prim(d, c->th, c->ns, c->cop, U, U1, d.red + XF_RED_DT, flag, 1, nflags, c->stream, &c->launches));
+					return XF_OK;
 				}
 				KL(c->t->rk(d, c->E, U, U1, LU, 0.0, d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
 				c->launches++;
@@ -839,7 +874,9 @@ extern "C"
 		c->launches++;
 		return XF_OK;
 	}
-	int xf_rk_stage(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int flag)
+	// deep_valid: the previous stage's k_rk_prim has recovered the deep cells of this stage's input; fuse_next: this stage's update does the
+	// same for the next stage (whose input is U1 after stages 1 and 2, U after stage 3: stage 1 of the next step)
+	static int rk_stage_ex(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int flag, bool deep_valid, bool fuse_next)
 	{
 		if (flag < 1 || flag > 3)
 			return fail(XF_ERR_ARG, "flag must be 1..3");
@@ -849,11 +886,12 @@ extern "C"
 			return rc;
 		// the dt of the NEXT step is computed from the primitives of stage 3 (XFLUIDS.cpp:196 reads fdata as left
 		// by the last UpdateStates) -> gather the maxima there
-		if ((rc = update_states(c, UI, flag == 3)))
+		if ((rc = deep_valid ? update_states_shell(c, UI, flag == 3) : update_states(c, UI, flag == 3)))
 			return rc;
 		// x, y sweeps accumulate their part of the divergence in LU; the last direction adds its own and applies NaN guard + RK update
-		return stage_sweeps(c, U, U1, LU, flag, 7, -1, -1, -1, -1, true);
+		return stage_sweeps(c, U, U1, LU, flag, 7, -1, -1, -1, -1, true, fuse_next ? prim_flags(c, flag == 2) : -1);
 	}
+	int xf_rk_stage(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int flag) { return rk_stage_ex(c, U, U1, LU, bc, flag, false, false); }
 	// ---- one stage split around the z-halo exchange (multi-GPU overlap; include/xfluids_b200.h) --------------
 	int xf_stage_interior(xf_ctx *c, double *U, double *U1, double *LU, int flag)
 	{
@@ -913,57 +951,71 @@ extern "C"
 		return XF_OK;
 	}
 
-	static int enqueue_step(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], double t_end)
+	// first_valid: the deep cells of U are already recovered (by the previous step of the batch); fuse_last: leave them so for the next
+	static int enqueue_step(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], double t_end, bool first_valid = false, bool fuse_last = false)
 	{
 		int rc;
+		const bool fuse = can_fuse(c);
 		if ((rc = xf_dt_device(c, t_end)))
 			return rc;
 		for (int flag = 1; flag <= 3; flag++)
-			if ((rc = xf_rk_stage(c, U, U1, LU, bc, flag)))
+			if ((rc = rk_stage_ex(c, U, U1, LU, bc, flag, fuse && (flag > 1 || first_valid), fuse && (flag < 3 || fuse_last))))
 				return rc;
+		return XF_OK;
+	}
+	static int capture_step(xf_ctx *c, int which, double *U, double *U1, double *LU, const int bc[6], double t_end)
+	{
+		cudaStream_t cap = c->stream;
+		cudaStream_t own = nullptr;
+		if (cap == nullptr)
+		{ // the legacy default stream cannot be captured
+			CU(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+			CU(cudaStreamSynchronize(nullptr));
+			c->stream = own;
+		}
+		const long long l0 = c->launches;
+		CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+		int rc = enqueue_step(c, U, U1, LU, bc, t_end, (which & 1) != 0, (which & 2) != 0);
+		cudaGraph_t g = nullptr;
+		cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+		c->glaunches[which] = c->launches - l0;
+		c->launches = l0;
+		if (own)
+			c->stream = cap;
+		if (rc || e != cudaSuccess)
+		{
+			if (own)
+				cudaStreamDestroy(own);
+			return rc ? rc : fail(XF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+		}
+		CU(cudaGraphInstantiate(&c->gexec[which], g, 0));
+		CU(cudaGraphDestroy(g));
+		if (own)
+			CU(cudaStreamDestroy(own));
 		return XF_OK;
 	}
 	int xf_run(xf_ctx *c, double *U, double *U1, double *LU, const int bc[6], int nsteps, double t_end, int *steps_done, double *time_out, int *error)
 	{
 		CU(cudaSetDevice(c->device));
 		// (re)capture one step when pointers / BCs / t_end change
-		const bool same = c->gexec && c->gU == U && c->gU1 == U1 && c->gLU == LU && c->gt_end == t_end && !std::memcmp(c->gbc, bc, 6 * sizeof(int));
+		const bool same = c->gU == U && c->gU1 == U1 && c->gLU == LU && c->gt_end == t_end && !std::memcmp(c->gbc, bc, 6 * sizeof(int));
 		if (!same)
 		{
-			if (c->gexec)
-				cudaGraphExecDestroy(c->gexec), c->gexec = nullptr;
-			cudaStream_t cap = c->stream;
-			cudaStream_t own = nullptr;
-			if (cap == nullptr)
-			{ // the legacy default stream cannot be captured
-				CU(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
-				CU(cudaStreamSynchronize(nullptr));
-				c->stream = own;
-			}
-			const long long l0 = c->launches;
-			CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-			int rc = enqueue_step(c, U, U1, LU, bc, t_end);
-			cudaGraph_t g = nullptr;
-			cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-			c->glaunches = c->launches - l0;
-			c->launches = l0;
-			if (own)
-				c->stream = cap;
-			if (rc || e != cudaSuccess)
-			{
-				if (own)
-					cudaStreamDestroy(own);
-				return rc ? rc : fail(XF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-			}
-			CU(cudaGraphInstantiate(&c->gexec, g, 0));
-			CU(cudaGraphDestroy(g));
-			if (own)
-				CU(cudaStreamDestroy(own));
+			c->drop_graphs();
 			c->gU = U, c->gU1 = U1, c->gLU = LU, c->gt_end = t_end;
 			std::memcpy(c->gbc, bc, 6 * sizeof(int));
 		}
+		const bool fuse = can_fuse(c);
 		double t = 0, dt = 0;
 		int rc, queued = 0, err = 0;
+		auto replay = [&](int which) -> int
+		{
+			if (!c->gexec[which] && (rc = capture_step(c, which, U, U1, LU, bc, t_end)))
+				return rc;
+			CU(cudaGraphLaunch(c->gexec[which], c->stream));
+			c->launches += c->glaunches[which];
+			return XF_OK;
+		};
 		if ((rc = xf_get_time(c, &t, nullptr)))
 			return rc;
 		const long long steps0 = steps_taken(c);
@@ -971,9 +1023,11 @@ extern "C"
 		while (queued < nsteps && t < t_end)
 		{
 			int batch = poll < nsteps - queued ? poll : nsteps - queued;
+			// every batch starts from and ends in the state the reference's loop has between steps (U as the stage-3 update left it):
+			// only inside a batch does the stage-3 update go on to the next step's recovery
 			for (int s = 0; s < batch; s++)
-				CU(cudaGraphLaunch(c->gexec, c->stream));
-			c->launches += c->glaunches * batch;
+				if ((rc = replay((fuse && batch > 1) ? (s == 0 ? 2 : (s == batch - 1 ? 1 : 3)) : 0)))
+					return rc;
 			queued += batch;
 			int f[4];
 			if ((rc = xf_get_time(c, &t, &dt)) || (rc = xf_error_flags(c, f)))
@@ -1011,6 +1065,7 @@ extern "C"
 		for (int i = 0; i < NE; i++)
 			CU(cudaEventCreate(&ev[i]));
 		int e = 0, rc;
+		const bool fuse = can_fuse(c);
 		CU(cudaEventRecord(ev[e++], c->stream));
 		if ((rc = xf_dt_device(c, t_end)))
 			return rc;
@@ -1021,7 +1076,7 @@ extern "C"
 			if ((rc = xf_boundary(c, UI, bc)))
 				return rc;
 			CU(cudaEventRecord(ev[e++], c->stream));
-			if ((rc = update_states(c, UI, flag == 3)))
+			if ((rc = (fuse && flag > 1) ? update_states_shell(c, UI, flag == 3) : update_states(c, UI, flag == 3)))
 				return rc;
 			const int last_dir = c->d.DimZ ? 2 : (c->d.DimY ? 1 : 0);
 			for (int dir = 0; dir < 3; dir++)
@@ -1033,8 +1088,20 @@ extern "C"
 			CU(cudaEventRecord(ev[e++], c->stream));
 			if (c->tiled)
 			{
-				KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
-				c->launches++;
+				if (c->vs.on)
+					KL(c->t->visc(c->d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches));
+				if (fuse && flag < 3)
+				{ // the step as xf_run's self-contained graph runs it: ms[6] holds the deep cells' recovery of stages 2 and 3, ms[2] the rest
+					const int nflags = prim_flags(c, flag == 2);
+					if (nflags & 1)
+						CU(cudaMemsetAsync(c->d.red + XF_RED_DTMAX, 0, 3 * sizeof(double), c->stream));
+					KL(c->t->rk_prim(c->d, c->th, c->ns, c->cop, U, U1, c->d.red + XF_RED_DT, flag, 1, nflags, c->stream, &c->launches));
+				}
+				else
+				{
+					KL(c->t->rk(c->d, c->E, U, U1, LU, 0.0, c->d.red + XF_RED_DT, flag, 1, 1, c->stream, -1, -1));
+					c->launches++;
+				}
 			}
 		}
 		CU(cudaEventRecord(ev[e++], c->stream));

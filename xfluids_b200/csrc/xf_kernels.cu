@@ -290,10 +290,11 @@ __device__ __forceinline__ void prim_cell(const XfDev &d, const XfThermo &th, do
 // ncu (source-level sampling) had 30 % of this kernel's samples on the first use of the cell's freshly loaded U -- DRAM latency that
 // 20 resident warps per SM cannot hide -- hence the cp.async double buffer: each thread prefetches ITS OWN next cell (no barrier).
 template <class C>
-__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0 /* first z-plane */, long long lin1)
+__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th, double *__restrict__ U, int flags, long long lin0 /* first z-plane */, long long lin1,
+																	 int split = 0x7fffffff, int gap = 0 /* planes lin0 + y, skipping `gap` planes from the split-th on */)
 {
 	constexpr int E = C::E, NV = E + (C::COP ? 1 : 0), CH = XF_PRIM_PIPE > 0 ? XF_PRIM_PIPE : 1;
-	const int kq = int(lin0) + int(blockIdx.y);
+	const int kq = int(lin0) + int(blockIdx.y) + (int(blockIdx.y) >= split ? gap : 0);
 	const long long pbase = (long long)kq * d.sZ;
 	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	(void)lin1;
@@ -349,6 +350,46 @@ __global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim(XfDev d, XfThermo th
 #endif
 		if (active)
 			prim_cell<C>(d, th, U, pbase + q, int(iq), int(jq), kq, Uc, Tc, flags, dtm, glf);
+	}
+	prim_reduce(d, flags, dtm, glf);
+}
+
+// Primitive recovery of the shell of the middle z-planes [dp.zlo, dp.zhi): the rows outside [ylo, yhi) whole, of the others the cells
+// outside [xlo, xhi).  (The planes outside [zlo, zhi) are whole planes: k_prim.)
+template <class C>
+__global__ void __launch_bounds__(128, XF_PRIM_MINB) k_prim_shell(XfDev d, XfThermo th, XfDeep dp, double *__restrict__ U, int flags)
+{
+	constexpr int E = C::E;
+	const int kq = dp.zlo + int(blockIdx.y);
+	const unsigned t = blockIdx.x * 128u + threadIdx.x;
+	const unsigned nfull = unsigned(dp.ylo + (d.Ymax - dp.yhi)) * unsigned(d.Xp), nside = unsigned(dp.xlo + (d.Xmax - dp.xhi));
+	int i, j;
+	bool active;
+	if (t < nfull)
+	{
+		const unsigned jr = t / unsigned(d.Xp);
+		i = int(t - jr * unsigned(d.Xp));
+		j = int(jr) < dp.ylo ? int(jr) : dp.yhi + (int(jr) - dp.ylo);
+		active = i < d.Xmax;
+	}
+	else
+	{
+		const unsigned q = t - nfull, jr = nside ? q / nside : 0u, ii = nside ? q - jr * nside : 0u;
+		j = dp.ylo + int(jr);
+		i = int(ii) < dp.xlo ? int(ii) : dp.xhi + (int(ii) - dp.xlo);
+		active = nside > 0 && j < dp.yhi;
+	}
+	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (active)
+	{
+		const long long id = ((long long)kq * d.Ymax + j) * d.Xp + i;
+		double Uc[E], Tc = 0.0;
+#pragma unroll
+		for (int n = 0; n < E; n++)
+			Uc[n] = U[n * d.N + id];
+		if constexpr (C::COP)
+			Tc = d.T[id];
+		prim_cell<C>(d, th, U, id, i, j, kq, Uc, Tc, flags, dtm, glf);
 	}
 	prim_reduce(d, flags, dtm, glf);
 }
@@ -839,6 +880,55 @@ __global__ void __launch_bounds__(256) k_rk(XfDev d, double *__restrict__ U, dou
 	if (guard && bad)
 		d.err[2] = 1;
 }
+// k_rk_prim: the stage update of k_rk<E, true> going straight on to the NEXT stage's primitive recovery for the deep cells (XfDeep), whose
+// updated conserved variables are still in registers.  Shell cells are only updated; BC fill and k_prim_shell follow.  nflags: the
+// gather flags of the next stage's recovery.  Same block order as k_rk (the wall fluxes of the lower faces come out of L2).
+#ifndef XF_RKP_MINB
+#define XF_RKP_MINB 4
+#endif
+template <class C>
+__global__ void __launch_bounds__(128, XF_RKP_MINB) k_rk_prim(XfDev d, XfThermo th, XfDeep dp, double *__restrict__ U, double *__restrict__ U1,
+															   const double *__restrict__ dt_dev, int flag, int guard, int nflags)
+{
+	constexpr int E = C::E;
+	long long id;
+	double dtm[3] = {0.0, 0.0, 0.0}, glf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (inner_cell_zfast(d, id, 0, d.Zi))
+	{
+		const int i = int(id % d.Xp);
+		const long long row = id / d.Xp;
+		const int j = int(row % d.Ymax), k = int(row / d.Ymax);
+		const bool deep = i >= dp.xlo && i < dp.xhi && j >= dp.ylo && j < dp.yhi && k >= dp.zlo && k < dp.zhi;
+		const double dt = *dt_dev;
+		double *__restrict__ UO = (flag == 3) ? U : U1;
+		double Un[E], Tc = 0.0;
+		if constexpr (C::COP)
+			if (deep)
+				Tc = d.T[id];
+		bool bad = false;
+#pragma unroll
+		for (int n = 0; n < E; n++)
+		{
+			const long long o = n * d.N + id;
+			const double lu = lu_of(d, o);
+			const double u0 = U[o];
+			const double u1 = (flag == 1) ? 0.0 : U1[o];
+			if (guard)
+			{
+				const double ui = (flag == 3) ? u0 : ((flag == 1) ? U1[o] : u1);
+				bad = bad || isnan(ui) || isinf(ui) || isnan(lu) || isinf(lu) || (n == 0 && ui < 0);
+			}
+			Un[n] = rk_of(u0, u1, lu, dt, flag);
+			if (!(C::COP && n >= 5 && d.ghost && deep)) // GhostSpecies: the recovery stores the renormalised partial densities
+				UO[o] = Un[n];
+		}
+		if (guard && bad)
+			d.err[2] = 1;
+		if (deep)
+			prim_cell<C>(d, th, UO, id, i, j, k, Un, Tc, nflags, dtm, glf);
+	}
+	prim_reduce(d, nflags, dtm, glf);
+}
 template <int E>
 __global__ void __launch_bounds__(256) k_nan(XfDev d, const double *__restrict__ UI, const double *__restrict__ LU)
 {
@@ -1203,6 +1293,65 @@ static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *
 	default: return -1;                                 \
 	}
 
+// primitive recovery of every cell outside the deep set (after the ghost fill); the list of unconverged cells is NOT reset: the deep
+// cells' entries (k_rk_prim) are still in it, k_prim_hard finishes both
+template <class C>
+static int prim_shell_t(const XfDev &d, const XfThermo &th, double *U, int flags, cudaStream_t s, long long *launches)
+{
+	const XfDeep dp = xf_deep_cells(d);
+	constexpr int CHB = 128 * (XF_PRIM_PIPE > 0 ? XF_PRIM_PIPE : 1);
+	const int nslab = dp.zlo + (d.Zmax - dp.zhi), nmid = dp.zhi - dp.zlo;
+	if (nslab > 0)
+	{
+		k_prim<C><<<dim3((unsigned)((d.sZ + CHB - 1) / CHB), (unsigned)nslab), 128, 0, s>>>(d, th, U, flags, 0LL, 0LL, dp.zlo, nmid);
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
+	if (nmid > 0)
+	{
+		const long long per = (long long)(dp.ylo + (d.Ymax - dp.yhi)) * d.Xp + (long long)(dp.yhi - dp.ylo) * (dp.xlo + (d.Xmax - dp.xhi));
+		if (per > 0)
+		{
+			k_prim_shell<C><<<dim3((unsigned)((per + 127) / 128), (unsigned)nmid), 128, 0, s>>>(d, th, dp, U, flags);
+			XF_CHECK_LAUNCH();
+			++*launches;
+		}
+	}
+	if constexpr (C::COP)
+	{
+		k_prim_hard<C><<<d.nsm * 8, 128, 0, s>>>(d, th, U, flags);
+		XF_CHECK_LAUNCH();
+		++*launches;
+	}
+	return 0;
+}
+template <class C>
+static int rk_prim_t(const XfDev &d, const XfThermo &th, double *U, double *U1, const double *dt_dev, int flag, int guard, int nflags, cudaStream_t s, long long *launches)
+{
+	if constexpr (C::COP)
+	{
+		cudaError_t e = cudaMemsetAsync(d.hard_count, 0, sizeof(unsigned), s);
+		if (e != cudaSuccess)
+			return (int)e;
+	}
+	constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 1;
+	long long nb = (long long)((d.Xi + 127) / 128) * d.Yi * d.Zi;
+	if (XF_RK_TILE > 0)
+		nb = (long long)((d.Xi + 127) / 128) * ((d.Yi + TT - 1) / TT) * ((d.Zi + TT - 1) / TT) * (TT * TT);
+	k_rk_prim<C><<<(unsigned)nb, 128, 0, s>>>(d, th, xf_deep_cells(d), U, U1, dt_dev, flag, guard, nflags);
+	XF_CHECK_LAUNCH();
+	++*launches;
+	return 0;
+}
+int launch_prim_shell(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches)
+{
+	XF_DISPATCH_CFG(ns, cop, return prim_shell_t<C>(d, th, U, flags, s, launches));
+}
+int launch_rk_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, double *U1, const double *dt_dev, int flag, int guard, int nflags, cudaStream_t s,
+				   long long *launches)
+{
+	XF_DISPATCH_CFG(ns, cop, return rk_prim_t<C>(d, th, U, U1, dt_dev, flag, guard, nflags, s, launches));
+}
 int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1)
 {
 	XF_DISPATCH_CFG(ns, cop, return prim_t<C>(d, th, U, flags, s, launches, k0, k1));

@@ -15,6 +15,9 @@ struct XfTma
 	namespace NS                                                                                                              \
 	{                                                                                                                         \
 		int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches, int k0, int k1); \
+		int launch_prim_shell(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, int flags, cudaStream_t s, long long *launches); \
+		int launch_rk_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, double *U1, const double *dt_dev, int flag, int guard, int nflags, \
+						   cudaStream_t s, long long *launches);                                                            \
 		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, \
 						  const CUtensorMap *tmy, const CUtensorMap *tmz);                                                      \
 		int xf_z_tiles(const XfDev &d);                                                                                       \

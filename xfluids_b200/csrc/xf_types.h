@@ -87,6 +87,24 @@ struct XfVisc
 };
 
 // arguments of one sweep launch beyond the block description (k_sweep x direction, k_march y / z)
+// Cells no ghost fill / halo pack reads: at least one more ghost width away from every face of the inner block.  The stage update can go
+// straight on to their primitive recovery (k_rk_prim); the shell around them waits for the ghost fill (k_prim_shell).  GhostSpecies
+// renormalisation rewrites U, so a cell must be recovered exactly once per stage and only after every reader of its raw update is done.
+struct XfDeep
+{
+	int xlo, xhi, ylo, yhi, zlo, zhi; // deep cells: [xlo, xhi) x [ylo, yhi) x [zlo, zhi) in array indices (empty: all lo = hi = max)
+};
+static inline XfDeep xf_deep_cells(const XfDev &d)
+{
+	XfDeep p;
+	p.xlo = d.DimX ? 2 * d.Bx : 0, p.xhi = d.DimX ? d.Xmax - 2 * d.Bx : d.Xmax;
+	p.ylo = d.DimY ? 2 * d.By : 0, p.yhi = d.DimY ? d.Ymax - 2 * d.By : d.Ymax;
+	p.zlo = d.DimZ ? 2 * d.Bz : 0, p.zhi = d.DimZ ? d.Zmax - 2 * d.Bz : d.Zmax;
+	if (p.xhi <= p.xlo || p.yhi <= p.ylo || p.zhi <= p.zlo)
+		p.xlo = p.xhi = d.Xmax, p.ylo = p.yhi = d.Ymax, p.zlo = p.zhi = d.Zmax;
+	return p;
+}
+
 struct XfMarchArgs
 {
 	int mode;             // XF_MODE_FW / ACC / RK
