@@ -247,6 +247,10 @@ int xf_measure_pcie(xf_ctx *ctx, void *h_pinned, size_t bytes, double *h2d_gbs, 
  * table-driven algorithm so that it matches the reference CPU path bit for bit (csrc/xf_log.cuh); this entry point lets the
  * tests prove it against the host libm. */
 int xf_log_eval(int device, const double *h_x, double *h_y, size_t n);
+/* the same for the three transcendental functions of the viscous block's transport fits (reference
+ * src/solver_Reconstruction/viscosity/Visc_device.h:10-41): which = 0 log(x), 1 exp(x), 2 pow(x, y2) -- the device versions replay
+ * glibc's table-driven algorithms (csrc/xf_log.cuh, csrc/xf_exp.cuh); h_y2 may be null unless which = 2. */
+int xf_math_eval(int device, int which, const double *h_x, const double *h_y2, double *h_out, size_t n);
 
 /* kernel launch counter (bench.py "gpu_launches") */
 long long xf_launch_count(const xf_ctx *ctx);

@@ -1381,6 +1381,17 @@ extern "C"
 			y[i] = f(x[i]);
 	}
 
+	// the same for exp (which = 1) and pow (which = 2, exponents in y2): the transport fits' functions (Visc_device.h:10-41)
+	void xo_libm_eval(int which, const double *x, const double *y2, double *y, size_t n)
+	{
+		double (*volatile fe)(double) = std::exp;
+		double (*volatile fl)(double) = std::log;
+		double (*volatile fp)(double, double) = std::pow;
+#pragma omp parallel for
+		for (long long i = 0; i < (long long)n; i++)
+			y[i] = which == 0 ? fl(x[i]) : (which == 1 ? fe(x[i]) : fp(x[i], y2[i]));
+	}
+
 	xo_state *xo_state_create(const xo_cfg *c)
 	{
 		xo_state *s = (xo_state *)std::calloc(1, sizeof(xo_state));

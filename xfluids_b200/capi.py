@@ -95,6 +95,7 @@ _PROTOS = {
     "xf_profile_step": (C.c_int, [_P, _P, _P, _P, _BC, C.c_double, C.c_float * 8]),
     "xf_measure_peaks": (C.c_int, [C.c_int, _DP, _DP]),
     "xf_log_eval": (C.c_int, [C.c_int, _P, _P, C.c_size_t]),
+    "xf_math_eval": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_size_t]),
     "xf_measure_pcie": (C.c_int, [_P, _P, C.c_size_t, _DP, _DP]),
     "xf_measure_fp64_issue": (C.c_int, [C.c_int, C.c_double * 3]),
     "xf_slab_last_error": (C.c_char_p, []),
@@ -177,6 +178,17 @@ def log_eval(x, device=0):
     y = np.empty_like(x)
     L.check(L.dll.xf_log_eval(device, _dptr(x), _dptr(y), x.size))
     return y
+
+
+def math_eval(which, x, y2=None, device=0):
+    """Device log (0) / exp (1) / pow (2; exponents y2) of host arrays (csrc/xf_log.cuh, csrc/xf_exp.cuh), evaluated on `device`."""
+    L = Lib.get()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    if y2 is not None:
+        y2 = np.ascontiguousarray(np.broadcast_to(np.asarray(y2, dtype=np.float64), x.shape))
+    L.check(L.dll.xf_math_eval(device, which, _dptr(x), _dptr(y2) if y2 is not None else None, _dptr(out), x.size))
+    return out
 
 
 class Engine:

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -12,6 +13,7 @@
 #include "../../include/xfluids_b200.h"
 #include "xf_launch.h"
 #include "xf_log.cuh"
+#include "xf_exp.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &m)
@@ -174,6 +176,13 @@ __global__ void __launch_bounds__(256) k_log_eval(const double *__restrict__ x, 
 		y[i] = xf_log(x[i]);
 }
 
+// which: 0 log(x), 1 exp(x), 2 pow(x, y)
+__global__ void __launch_bounds__(256) k_math_eval(const double *__restrict__ x, const double *__restrict__ y2, double *__restrict__ y, size_t n, int which)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		y[i] = which == 0 ? xf_log(x[i]) : (which == 1 ? xf_exp(x[i]) : xf_pow(x[i], y2[i]));
+}
+
 extern "C"
 {
 	static int ensure_fw(xf_ctx *c);
@@ -199,6 +208,32 @@ extern "C"
 		cudaFree(dx), cudaFree(dy);
 		if (e != cudaSuccess)
 			return fail(XF_ERR_CUDA, std::string("xf_log_eval: ") + cudaGetErrorString(e));
+		return XF_OK;
+	}
+
+	int xf_math_eval(int device, int which, const double *h_x, const double *h_y2, double *h_out, size_t n)
+	{
+		CU(cudaSetDevice(device));
+		if (which < 0 || which > 2 || (which == 2 && !h_y2))
+			return fail(XF_ERR_ARG, "xf_math_eval: which = 0 (log), 1 (exp), 2 (pow, needs the exponents)");
+		double *dx = nullptr, *dy = nullptr, *d2 = nullptr;
+		cudaError_t e = cudaMalloc((void **)&dx, n * sizeof(double));
+		if (e == cudaSuccess)
+			e = cudaMalloc((void **)&dy, n * sizeof(double));
+		if (e == cudaSuccess && which == 2)
+			e = cudaMalloc((void **)&d2, n * sizeof(double));
+		if (e == cudaSuccess)
+			e = cudaMemcpy(dx, h_x, n * sizeof(double), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess && which == 2)
+			e = cudaMemcpy(d2, h_y2, n * sizeof(double), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess)
+		{
+			k_math_eval<<<1184, 256>>>(dx, d2, dy, n, which);
+			e = cudaMemcpy(h_out, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
+		}
+		cudaFree(dx), cudaFree(dy), cudaFree(d2);
+		if (e != cudaSuccess)
+			return fail(XF_ERR_CUDA, std::string("xf_math_eval: ") + cudaGetErrorString(e));
 		return XF_OK;
 	}
 
@@ -548,6 +583,16 @@ extern "C"
 						v.fit_Dkj[n * ns + q][m] = tr->fit_Dkj[(n * ns + q) * 4 + m];
 		}
 		v.Yil_limiter = tr->Yil_limiter, v.Dim_limiter = tr->Dim_limiter, v.dim_max0 = tr->dim_max0;
+		// the molar-mass factors of PHI are per-pair constants: evaluated here with the host's pow(), the function the reference calls
+		v.dkj_sym = v.diffu ? 1 : 0;
+		for (int k = 0; k < ns; k++)
+			for (int i = 0; i < ns; i++)
+			{
+				v.phiW[k * ns + i] = std::pow(v.Wi[i] / v.Wi[k], 0.25);
+				v.phiS[k * ns + i] = std::pow(1.0 + v.Wi[k] / v.Wi[i], -0.5);
+				if (v.diffu && std::memcmp(v.fit_Dkj[i * ns + k], v.fit_Dkj[k * ns + i], 4 * sizeof(double)) != 0)
+					v.dkj_sym = 0;
+			}
 		if (!was_on || !v.Vde)
 		{
 			const size_t N = (size_t)c->d.N;

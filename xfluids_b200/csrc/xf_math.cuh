@@ -13,6 +13,7 @@
 #pragma once
 #include "xf_types.h"
 #include "xf_log.cuh"
+#include "xf_exp.cuh"
 
 #define XF_DEV __device__ __forceinline__
 #if !defined(XF_THERMO_STATIC) && !defined(XF_THERMO_DYN)

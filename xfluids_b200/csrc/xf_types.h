@@ -77,6 +77,10 @@ struct XfVisc
 	double fit_visc[XF_MAXS][4], fit_therm[XF_MAXS][4]; // ln(mu_k), ln(lambda_k)
 	double fit_Dkj[XF_MAXS * XF_MAXS][4];               // ln(p D_kj)
 	double Wi[XF_MAXS];                                 // kg/mol
+	// the two factors of PHI(k, i) (Visc_device.h:34-41) that depend on the molar masses only, from the host's pow():
+	// phiW[k * NS + i] = pow(W_i / W_k, 0.25), phiS[k * NS + i] = pow(1 + W_k / W_i, -0.5)
+	double phiW[XF_MAXS * XF_MAXS], phiS[XF_MAXS * XF_MAXS];
+	int dkj_sym;                                        // fit_Dkj[i][k] == fit_Dkj[k][i] bit for bit: each pair's coefficient is evaluated once
 	double Yil_limiter, Dim_limiter, dim_max0;          // Block::Yil_limiter / Dim_limiter (iniset.cpp:358-359); Dim_max before scaling (0: the single-process build's value)
 	// work arrays
 	double *Vde;   // [9][N] velocity derivatives, order ducx dvcx dwcx ducy dvcy dwcy ducz dvcz dwcz (global_setup.h VdeType)
@@ -86,7 +90,6 @@ struct XfVisc
 	double *lim;   // device doubles: [0..NS) yi_min, [NS..2NS) yi_max -> after k_visc_limits: [2NS..3NS) Yil_limiter, [3NS..4NS) Diffu_limiter
 };
 
-// arguments of one sweep launch beyond the block description (k_sweep x direction, k_march y / z)
 // Cells no ghost fill / halo pack reads: at least one more ghost width away from every face of the inner block.  The stage update can go
 // straight on to their primitive recovery (k_rk_prim); the shell around them waits for the ghost fill (k_prim_shell).  GhostSpecies
 // renormalisation rewrites U, so a cell must be recovered exactly once per stage and only after every reader of its raw update is done.
@@ -105,6 +108,7 @@ static inline XfDeep xf_deep_cells(const XfDev &d)
 	return p;
 }
 
+// arguments of one sweep launch beyond the block description (k_sweep x direction, k_march y / z)
 struct XfMarchArgs
 {
 	int mode;             // XF_MODE_FW / ACC / RK

@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(256) k_vde_bc(XfDev d, XfVisc vs, int bc_min, 
 }
 
 // ln(coefficient) = ((c3 L + c2) L + c1) L + c0 with L = ln T  (Viscosity / Thermal_conductivity / GetDkj, Visc_device.h:10-101)
-__device__ __forceinline__ double xf_fit(const double *c, double L) { return exp(((c[3] * L + c[2]) * L + c[1]) * L + c[0]); }
+static __device__ __noinline__ double xf_pow_half(double x) { return xf_pow(x, 0.5); }
+// (out of line: thirty inlined copies of exp() made k_transport stall on instruction fetch)
+static __device__ __noinline__ double xf_fit4(double c0, double c1, double c2, double c3, double L) { return xf_exp(((c3 * L + c2) * L + c1) * L + c0); } // glibc's exp, bit for bit (xf_exp.cuh)
+#define xf_fit(c, L) xf_fit4((c)[0], (c)[1], (c)[2], (c)[3], (L)) // by value: the coefficients live in the kernel-parameter bank
 
 // Gettransport_coeff_aver over ALL cells (Visc_kernels.hpp:219-241)
 template <class C>
@@ -168,13 +171,16 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 #pragma unroll
 	for (int n = 0; n < NS; n++)
 		X[n] = X[n] * _C_total;
-	// Get_transport_coeff_aver (Visc_device.h:107-177)
+	// Get_transport_coeff_aver (Visc_device.h:107-177).  The reference evaluates Viscosity(k), Viscosity(i) inside the pair loop and three
+	// pow() per pair; here every fit is evaluated once per cell, the two molar-mass powers are the host's (xf_set_transport), and log, exp
+	// and pow replay glibc's algorithms (xf_log.cuh, xf_exp.cuh): the same bits as the reference CPU path.
 	const double L = xf_log(T);
 	double mu[NS], lam[NS];
 #pragma unroll
 	for (int n = 0; n < NS; n++)
 		mu[n] = xf_fit(vs.fit_visc[n], L), lam[n] = vs.heat ? xf_fit(vs.fit_therm[n], L) : 0.0;
 	double va = 0.0, tca = 0.0;
+	const double sqrt2 = sqrt(2.0);
 #pragma unroll
 	for (int kk = 0; kk < NS; kk++)
 	{
@@ -182,9 +188,9 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 #pragma unroll
 		for (int ii = 0; ii < NS; ii++)
 		{ // PHI(specie_k, specie_i) (Visc_device.h:34-41)
-			double phi = pow(vs.Wi[ii] / vs.Wi[kk], 0.25) * pow(mu[kk] / mu[ii], 0.5);
-			phi = (phi + 1.0) * (phi + 1.0) * 0.5 / sqrt(2.0);
-			phi = phi * pow(1.0 + vs.Wi[kk] / vs.Wi[ii], -0.5);
+			double phi = vs.phiW[kk * NS + ii] * (ii == kk ? 1.0 : xf_pow_half(mu[kk] / mu[ii])); // pow(1, 0.5) == 1
+			phi = (phi + 1.0) * (phi + 1.0) * 0.5 / sqrt2;
+			phi = phi * vs.phiS[kk * NS + ii];
 			den = den + X[ii] * phi;
 		}
 		const double _den = 1.0 / den;
@@ -200,6 +206,19 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 		double Dk[NS];
 		if constexpr (NS > 1)
 		{
+			// (X_i + 1e-40) / (D_ik / p + 1e-40) per ordered pair; with bitwise symmetric fits (GetFitCoefficient's are) D_ik is D_ki
+			double Dp[NS][NS];
+#pragma unroll
+			for (int kk = 0; kk < NS; kk++)
+#pragma unroll
+				for (int ii = 0; ii < NS; ii++)
+					if (ii != kk)
+					{
+						if (ii > kk || !vs.dkj_sym)
+							Dp[kk][ii] = xf_fit(vs.fit_Dkj[ii * NS + kk], L) / p + 1.0e-40;
+						else
+							Dp[kk][ii] = Dp[ii][kk];
+					}
 #pragma unroll
 			for (int kk = 0; kk < NS; kk++)
 			{
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 					if (ii != kk)
 					{
 						temp1 += (X[ii] + 1.0e-40) * vs.Wi[ii];
-						temp2 += (X[ii] + 1.0e-40) / (xf_fit(vs.fit_Dkj[ii * NS + kk], L) / p + 1.0e-40);
+						temp2 += (X[ii] + 1.0e-40) / Dp[kk][ii];
 					}
 				// sycl::step(ceil(temp1), 0.0) == 1 <=> 0.0 >= ceil(temp1)
 				if (!(0.0 < ceil(temp1)))
@@ -290,22 +309,13 @@ __global__ void k_visc_limits(XfVisc vs, int NS)
 	vs.lim[2 * NS + n] = ymax, vs.lim[3 * NS + n] = dmax;
 }
 
-// GetWallViscousFlux{X,Y,Z}: Flux_wall -= F_wall_v at the faces of direction DIR
+// GetWallViscousFlux{X,Y,Z}: Flux_wall -= F_wall_v at the face of direction DIR above cell id
 template <class C, int DIR>
-__global__ void __launch_bounds__(128) k_visc_flux(XfDev d, XfVisc vs, const double *__restrict__ U, double *__restrict__ Fw)
+__device__ __forceinline__ void visc_face(const XfDev &d, const XfVisc &vs, const double *__restrict__ U, double *__restrict__ Fw, const long long id)
 {
 	constexpr int NS = C::NS, E = C::E;
-	// faces: (inner + 1) along DIR starting at B - 1, inner in the other directions
-	const int n0 = d.Xi + (DIR == 0), n1 = d.Yi + (DIR == 1), n2 = d.Zi + (DIR == 2);
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int ii = int(t % n0);
-	const long long r = t / n0;
-	const int jj = int(r % n1), kk = int(r / n1);
-	if (kk >= n2)
-		return;
-	const int i = ii + d.Bx - (DIR == 0), j = jj + d.By - (DIR == 1), k = kk + d.Bz - (DIR == 2);
 	const long long s = DIR == 0 ? 1 : (DIR == 1 ? d.sY : d.sZ);
-	const long long id = ((long long)k * d.Ymax + j) * d.Xp + i, id_m1 = id - s, id_p1 = id + s, id_p2 = id + 2 * s;
+	const long long id_m1 = id - s, id_p1 = id + s, id_p2 = id + 2 * s;
 	const double _sxtn = 1.0 / 16.0, _twfr = 1.0 / 24.0, _OT = 1.0 / 3.0;
 	const double _dl = DIR == 0 ? d._dx : (DIR == 1 ? d._dy : d._dz);
 	const double tX = d.DimX ? 1.0 : 0.0, tY = d.DimY ? 1.0 : 0.0, tZ = d.DimZ ? 1.0 : 0.0;
@@ -393,6 +403,35 @@ __global__ void __launch_bounds__(128) k_visc_flux(XfDev d, XfVisc vs, const dou
 		Fw[n * N + id] -= Fv[n];
 }
 
+// All three directions in one pass: one thread per cell of the box [B - 1, B + inner) of every active direction forms the viscous flux at
+// its upper x, y and z face (where that face exists: the other two indices inner).  The ~26 per-cell arrays the three stencils share
+// come from DRAM once instead of three times; blocks walk the (y, z) plane in tiles, z fastest (k_rk's order), so that the rows / planes a
+// stencil shares with its neighbours are in L1 / L2.
+template <class C>
+__global__ void __launch_bounds__(128) k_visc_flux3(XfDev d, XfVisc vs, const double *__restrict__ U)
+{
+	constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 8;
+	const int ny = d.Yi + (d.DimY ? 1 : 0), nz = d.Zi + (d.DimZ ? 1 : 0);
+	const int nty = (ny + TT - 1) / TT, ntz = (nz + TT - 1) / TT;
+	const unsigned per_x = unsigned(nty) * unsigned(ntz) * (TT * TT);
+	const int xc = int(blockIdx.x / per_x);
+	const unsigned r = unsigned(blockIdx.x - (long long)xc * per_x);
+	const unsigned tile = r / (TT * TT), w = r % (TT * TT);
+	const int kk = int(tile / nty) * TT + int(w % TT), jj = int(tile % nty) * TT + int(w / TT);
+	const int ii = xc * 128 + int(threadIdx.x);
+	if (jj >= ny || kk >= nz || ii >= d.Xi + (d.DimX ? 1 : 0))
+		return;
+	const int i = ii + d.Bx - (d.DimX ? 1 : 0), j = jj + d.By - (d.DimY ? 1 : 0), k = kk + d.Bz - (d.DimZ ? 1 : 0);
+	const long long id = ((long long)k * d.Ymax + j) * d.Xp + i;
+	const bool xin = i >= d.Bx, yin = j >= d.By, zin = k >= d.Bz;
+	if (d.DimX && yin && zin)
+		visc_face<C, 0>(d, vs, U, d.Fw[0], id);
+	if (d.DimY && xin && zin)
+		visc_face<C, 1>(d, vs, U, d.Fw[1], id);
+	if (d.DimZ && xin && yin)
+		visc_face<C, 2>(d, vs, U, d.Fw[2], id);
+}
+
 // the viscous block of GetLU (ConVenction_block.hpp:424-575) after the inviscid wall fluxes (and their limiter) are in Fw; U = the sweep input
 template <class C>
 static int visc_t(const XfDev &d, const XfThermo &th, const XfVisc &vs, const double *U, const int bc[6], cudaStream_t s, long long *launches)
@@ -417,22 +456,11 @@ static int visc_t(const XfDev &d, const XfThermo &th, const XfVisc &vs, const do
 		k_visc_limits<<<1, 32, 0, s>>>(vs, C::NS);
 		*launches += 2;
 	}
-	if (d.DimX)
 	{
-		const long long n = (long long)(d.Xi + 1) * d.Yi * d.Zi;
-		k_visc_flux<C, 0><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d, vs, U, d.Fw[0]);
-		++*launches;
-	}
-	if (d.DimY)
-	{
-		const long long n = (long long)d.Xi * (d.Yi + 1) * d.Zi;
-		k_visc_flux<C, 1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d, vs, U, d.Fw[1]);
-		++*launches;
-	}
-	if (d.DimZ)
-	{
-		const long long n = (long long)d.Xi * d.Yi * (d.Zi + 1);
-		k_visc_flux<C, 2><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d, vs, U, d.Fw[2]);
+		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 8;
+		const int nx = d.Xi + (d.DimX ? 1 : 0), ny = d.Yi + (d.DimY ? 1 : 0), nz = d.Zi + (d.DimZ ? 1 : 0);
+		const long long nb = (long long)((nx + 127) / 128) * ((ny + TT - 1) / TT) * ((nz + TT - 1) / TT) * (TT * TT);
+		k_visc_flux3<C><<<(unsigned)nb, 128, 0, s>>>(d, vs, U);
 		++*launches;
 	}
 	XF_CHECK_LAUNCH();
