@@ -519,6 +519,8 @@ def main():
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = "%s:%dx%dx%d:weno%d" % (args.workload, setup.block.X_inner, setup.block.Y_inner, setup.block.Z_inner, args.weno)
+            if getattr(args, "visc", 0):
+                key += ":visc"     # the sweeps carry the viscous wall fluxes in their tails: their own instruction counts
             if key in tj and top in tj[key]:
                 traffic, traffic_src = tj[key][top], tj.get("source")
                 executed = tj[key].get("executed")

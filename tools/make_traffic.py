@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PROF = os.path.join(os.path.dirname(HERE), "profiles")
 OPS = {  # tag of profiles/<round>_fp64ops_<tag>.csv (ncu --metrics ...op_d{add,mul,fma}... --csv of the sweeps) -> traffic.json key, faces
     "sbi512": "sbi:512x512x512:weno5", "w7": "sbi:512x512x512:weno7", "cu6pp": "sbi:512x512x512:weno6", "jet": "jet:1024x512x512:weno5",
-    "riemann": "riemann:4096x4096x1:weno5", "vortex": "vortex:1024x1024x1:weno5"}
+    "riemann": "riemann:4096x4096x1:weno5", "vortex": "vortex:1024x1024x1:weno5", "visc": "sbi:512x512x512:weno5:visc"}
 WORKLOADS = {  # summary file tag -> (traffic.json key, faces per sweep launch by direction)
     "sbi512": ("sbi:512x512x512:weno5", {"x": 513 * 512 * 512, "y": 512 * 513 * 512, "z": 512 * 512 * 513}),
     "w7": ("sbi:512x512x512:weno7", {"x": 513 * 512 * 512, "y": 512 * 513 * 512, "z": 512 * 512 * 513}),

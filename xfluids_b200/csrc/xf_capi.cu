@@ -103,6 +103,9 @@ struct xf_ctx
 	// measured SLOWER than the two kernels (SBI 512^3: 29.4 ms against 9.9 + 10.7 ms per stage, profiles/r02_tuning.md): at the 128
 	// registers the recovery needs, 16 warps per SM cannot keep the update's 73 loads per cell in flight
 	int fuse = 0;
+	// 1 (default; XF_VISC_TAIL=0 switches it off): with the viscous terms on, every sweep of a whole-stage call subtracts the viscous wall
+	// flux of its face before it stores, instead of a separate kernel that reads and rewrites the three wall-flux fields
+	int visc_tail = 1;
 	void drop_graphs()
 	{
 		for (int i = 0; i < 4; i++)
@@ -297,6 +300,8 @@ extern "C"
 		c->tiled = (march && march[0] == '1') ? 0 : 1;
 		const char *fuse = std::getenv("XF_FUSE_PRIM");
 		c->fuse = (fuse && fuse[0] == '1') ? 1 : 0;
+		const char *vtail = std::getenv("XF_VISC_TAIL");
+		c->visc_tail = (vtail && vtail[0] == '0') ? 0 : 1;
 		// every failure from here on goes through one exit that releases what has been allocated; the first failure wins
 		int rc = 0;
 		auto alloc = [&](double **p, size_t n)
@@ -674,7 +679,8 @@ extern "C"
 		return 0;
 	}
 	// tiled sweeps of `dirmask` (wall fluxes stored in Fw)
-	static int tiled_sweeps(xf_ctx *c, const double *UI, int dirmask, int kp0, int kp1, int tz0, int tz1)
+	// visc_tail: every sweep subtracts the viscous wall flux before it stores (the viscous prelude has run on this stage's primitives)
+	static int tiled_sweeps(xf_ctx *c, const double *UI, int dirmask, int kp0, int kp1, int tz0, int tz1, bool visc_tail = false)
 	{
 		const CUtensorMap *tmy = nullptr, *tmz = nullptr;
 		int rc;
@@ -682,7 +688,8 @@ extern "C"
 			return rc;
 		if ((dirmask & 4) && c->d.DimZ && (rc = tile_map_for(c, UI, 2, &tmz)))
 			return rc;
-		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz));
+		const XfViscF vf = xf_visc_face_args(c->vs);
+		KL(c->t->sweeps(c->d, c->ns, c->cop, UI, c->stream, &c->launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz, visc_tail ? &vf : nullptr));
 		return XF_OK;
 	}
 
@@ -726,13 +733,19 @@ extern "C"
 			if (!allz)
 				return fail(XF_ERR_ARG, "the tiled sweeps cover whole blocks in z only");
 			int rc;
-			if ((rc = tiled_sweeps(c, UI, dirmask, kp0, kp1, -1, -1)))
+			// a whole stage in one call: the viscous prelude (derivatives, transport coefficients, limiter extrema) runs first and every sweep
+			// subtracts the viscous flux of its face before storing -- Fw is written once.  Split stages (z-slab overlap: the prelude needs the
+			// z-ghost primitives the x / y sweeps do not wait for) keep the stand-alone pass after the last sweep.
+			const bool tail = c->vs.on && c->visc_tail && finish && dirmask == 7;
+			if (tail)
+				KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches, 1));
+			if ((rc = tiled_sweeps(c, UI, dirmask, kp0, kp1, -1, -1, tail)))
 				return rc;
 			if (finish)
 			{
-				if (c->vs.on)
+				if (c->vs.on && !tail)
 				{ // viscous wall fluxes are subtracted once every direction's inviscid wall flux is in memory (ConVenction_block.hpp:424-575)
-					KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches));
+					KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches, 3));
 				}
 				if (nflags >= 0)
 				{
@@ -861,7 +874,7 @@ extern "C"
 			}
 		}
 		if (c->vs.on)
-			KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, U, c->gbc_stage, c->stream, &c->launches));
+			KL(c->t->visc(d, c->th, c->vs, c->ns, c->cop, U, c->gbc_stage, c->stream, &c->launches, 3));
 		KL(c->t->lu(c->d, c->E, LU, c->stream));
 		c->launches++;
 		return XF_OK;
@@ -1124,17 +1137,20 @@ extern "C"
 			if ((rc = (fuse && flag > 1) ? update_states_shell(c, UI, flag == 3) : update_states(c, UI, flag == 3)))
 				return rc;
 			const int last_dir = c->d.DimZ ? 2 : (c->d.DimY ? 1 : 0);
+			const bool tail = c->tiled && c->vs.on && c->visc_tail;
+			if (tail) // (lands in the "prim" bucket ms[2]; the wall-flux part is inside the sweeps' buckets)
+				KL(c->t->visc(c->d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches, 1));
 			for (int dir = 0; dir < 3; dir++)
 			{
 				CU(cudaEventRecord(ev[e++], c->stream));
-				if ((rc = c->tiled ? tiled_sweeps(c, UI, 1 << dir, -1, -1, -1, -1) : stage_sweeps(c, U, U1, LU, flag, 1 << dir, -1, -1, -1, -1, dir == last_dir)))
+				if ((rc = c->tiled ? tiled_sweeps(c, UI, 1 << dir, -1, -1, -1, -1, tail) : stage_sweeps(c, U, U1, LU, flag, 1 << dir, -1, -1, -1, -1, dir == last_dir)))
 					return rc;
 			}
 			CU(cudaEventRecord(ev[e++], c->stream));
 			if (c->tiled)
 			{
-				if (c->vs.on)
-					KL(c->t->visc(c->d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches));
+				if (c->vs.on && !tail)
+					KL(c->t->visc(c->d, c->th, c->vs, c->ns, c->cop, UI, c->gbc_stage, c->stream, &c->launches, 3));
 				if (fuse && flag < 3)
 				{ // the step as xf_run's self-contained graph runs it: ms[6] holds the deep cells' recovery of stages 2 and 3, ms[2] the rest
 					const int nflags = prim_flags(c, flag == 2);

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include "xf_math.cuh"
+#include "xf_visc_face.cuh"
 #include "xf_launch.h"
 #include "xf_tma.cuh"
 
@@ -580,10 +581,10 @@ constexpr int XF_TF = XF_TF_; // y/z sweeps: faces per tile along the sweep
 // ACC (x sweep of the marching path only): instead of storing the wall flux, write LU = 0.0 + (F_{i-1} - F_i) * _dx -- a compile-time
 // switch: as a run-time branch the extra tail cost the plain x sweep 6.7 % (75.6 vs 70.8 ms per step at 512^3; four 128-thread blocks
 // per SM at four places of a long instruction stream are sensitive to its length)
-template <class C, int DIR, int WENO, bool PP, bool ACC = false>
+template <class C, int DIR, int WENO, bool PP, bool ACC = false, bool VISC = false>
 __global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, DIR == 0 ? XfTx<WENO, PP>::MINB : XF_MINB_YZ) k_sweep(XfDev d, const __grid_constant__ CUtensorMap tmU /* y / z sweeps: the sweep input as a 4-D tensor, box = one tile's stencil rows */,
 		const double *__restrict__ U, double *__restrict__ Fw, int kp0 /* x / y sweeps: first z-plane of the plane range; z sweep: first tile of the tile range */,
-		double *__restrict__ LU /* ACC */)
+		double *__restrict__ LU /* ACC */, XfViscF vf = XfViscF() /* VISC: the viscous wall flux is subtracted before the store */)
 {
 	constexpr int mode = ACC ? XF_MODE_ACC : XF_MODE_FW;
 	constexpr int E = C::E, NST = XfStencil<WENO>::NST, P = XfStencil<WENO>::P, XF_TX = XfTx<WENO, PP>::V;
@@ -757,6 +758,14 @@ __global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, 
 	}
 	else
 	{
+		if constexpr (VISC)
+		{ // GetWallViscousFlux{X,Y,Z} (ConVenction_block.hpp:506-575): Flux_wall -= F_wall_v, after the limiter, on the flux still in registers
+			double Fv[E];
+			visc_face_flux<C, DIR>(d, vf, U, id_l, Fv);
+#pragma unroll
+			for (int n = 0; n < E; n++)
+				F[n] -= Fv[n];
+		}
 #pragma unroll
 		for (int n = 0; n < E; n++)
 			Fw[n * d.N + id_l] = F[n];
@@ -1153,7 +1162,8 @@ static int prim_t(const XfDev &d, const XfThermo &th, double *U, int flags, cuda
 // (the opt-in to > 48 KB of dynamic shared memory is per device and per kernel: set on every launch -- microseconds, no stream
 // operation, legal during graph capture -- rather than behind a per-process flag that would only cover the first device used)
 template <class C, int DIR, int WENO, bool PP>
-static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr)
+static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr,
+					  const XfViscF *vf = nullptr)
 {
 	static const CUtensorMap no_map{};
 	if (kp1 <= kp0)
@@ -1166,7 +1176,12 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, 
 		cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		const int cells = (mode == XF_MODE_FW) ? XF_TX : XF_TX - 1; // ACC: chunks overlap by one face
 		const dim3 g((unsigned)((d.sZ + cells - 1) / cells), (unsigned)(kp1 - kp0));
-		if (mode == XF_MODE_FW)
+		if (mode == XF_MODE_FW && vf)
+		{
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			k_sweep<C, DIR, WENO, PP, false, true><<<g, XF_TX, smem, s>>>(d, no_map, U, d.Fw[0], kp0, LU, *vf);
+		}
+		else if (mode == XF_MODE_FW)
 			k_sweep<C, DIR, WENO, PP, false><<<g, XF_TX, smem, s>>>(d, no_map, U, d.Fw[0], kp0, LU);
 		else
 		{
@@ -1185,22 +1200,29 @@ static int sweep_pp_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, 
 			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = (d.Yi + 1 + XF_TF - 1) / XF_TF, g.z = kp1 - kp0;
 		else
 			g.x = (d.Xi + XF_TW - 1) / XF_TW, g.y = kp1 - kp0, g.z = d.Yi; // kp0, kp1: tile range of the z sweep
-		k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, tm ? *tm : no_map, U, d.Fw[DIR], kp0, nullptr);
+		if (vf)
+		{
+			cudaFuncSetAttribute(k_sweep<C, DIR, WENO, PP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			k_sweep<C, DIR, WENO, PP, false, true><<<g, XF_TW * XF_TF, smem, s>>>(d, tm ? *tm : no_map, U, d.Fw[DIR], kp0, nullptr, *vf);
+		}
+		else
+			k_sweep<C, DIR, WENO, PP><<<g, XF_TW * XF_TF, smem, s>>>(d, tm ? *tm : no_map, U, d.Fw[DIR], kp0, nullptr);
 		(void)kp1;
 	}
 	XF_CHECK_LAUNCH();
 	return 0;
 }
 template <class C, int DIR, int WENO>
-static int sweep_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr)
+static int sweep_t(const XfDev &d, const double *U, cudaStream_t s, int kp0, int kp1, int mode = XF_MODE_FW, double *LU = nullptr, const CUtensorMap *tm = nullptr,
+				   const XfViscF *vf = nullptr)
 {
 #ifdef XF_ONLY_SBI
 	if (d.positivity || WENO != 5)
 		return -1;
 	if constexpr (WENO == 5)
-		return sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm);
+		return sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm, vf);
 #else
-	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s, kp0, kp1, mode, LU, tm) : sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm);
+	return d.positivity ? sweep_pp_t<C, DIR, WENO, true>(d, U, s, kp0, kp1, mode, LU, tm, vf) : sweep_pp_t<C, DIR, WENO, false>(d, U, s, kp0, kp1, mode, LU, tm, vf);
 #endif
 }
 // x sweep of the fused path: z-planes [a.t0, a.t1), a.mode = XF_MODE_ACC (LU = 0.0 + d/dx part) or XF_MODE_FW
@@ -1243,27 +1265,28 @@ static int march_t(const XfDev &d, const XfTma &tm, const double *UI, const XfMa
 // kp0, kp1: z-plane range [kp0, kp1) of the x and y sweeps (absolute plane indices inside [Bz, Bz + Zi)); the z sweep always
 // covers the block
 template <class C>
-static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, const CUtensorMap *tmy, const CUtensorMap *tmz)
+static int sweeps_t(const XfDev &d, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, const CUtensorMap *tmy, const CUtensorMap *tmz,
+					const XfViscF *vf)
 {
 	int rc = 0;
 	const bool dx = d.DimX && (dirmask & 1), dy = d.DimY && (dirmask & 2), dz = d.DimZ && (dirmask & 4);
 	if (d.weno == 7)
 	{
-		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 7>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, nullptr, vf), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 7>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy, vf), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 7>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz, vf), ++*launches;
 	}
 	else if (d.weno == 6)
 	{
-		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 6>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, nullptr, vf), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 6>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy, vf), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 6>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz, vf), ++*launches;
 	}
 	else
 	{
-		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s, kp0, kp1), ++*launches;
-		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy), ++*launches;
-		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz), ++*launches;
+		if (dx) rc |= sweep_t<C, 0, 5>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, nullptr, vf), ++*launches;
+		if (dy) rc |= sweep_t<C, 1, 5>(d, U, s, kp0, kp1, XF_MODE_FW, nullptr, tmy, vf), ++*launches;
+		if (dz) rc |= sweep_t<C, 2, 5>(d, U, s, tz0, tz1, XF_MODE_FW, nullptr, tmz, vf), ++*launches;
 	}
 	return rc;
 }
@@ -1360,18 +1383,18 @@ int launch_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, 
 // Bz - 1 + XF_TF t ... ; < 0: all xf_z_tiles() of them)
 int xf_z_tiles(const XfDev &d) { return (d.Zi + 1 + XF_TF - 1) / XF_TF; }
 int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1,
-				  const CUtensorMap *tmy, const CUtensorMap *tmz)
+				  const CUtensorMap *tmy, const CUtensorMap *tmz, const XfViscF *vf)
 {
 	if (kp0 < 0)
 		kp0 = d.Bz, kp1 = d.Bz + d.Zi;
 	if (tz0 < 0)
 		tz0 = 0, tz1 = xf_z_tiles(d);
-	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz));
+	XF_DISPATCH_CFG(ns, cop, return sweeps_t<C>(d, U, s, launches, dirmask, kp0, kp1, tz0, tz1, tmy, tmz, vf));
 }
 int z_tile_faces() { return XF_TF; }
-int launch_visc(const XfDev &d, const XfThermo &th, const XfVisc &vs, int ns, int cop, const double *U, const int bc[6], cudaStream_t s, long long *launches)
+int launch_visc(const XfDev &d, const XfThermo &th, const XfVisc &vs, int ns, int cop, const double *U, const int bc[6], cudaStream_t s, long long *launches, int parts)
 {
-	XF_DISPATCH_CFG(ns, cop, return visc_t<C>(d, th, vs, U, bc, s, launches));
+	XF_DISPATCH_CFG(ns, cop, return visc_t<C>(d, th, vs, U, bc, s, launches, parts));
 }
 int launch_sweep_x(const XfDev &d, int ns, int cop, const double *U, const XfMarchArgs &a, cudaStream_t s)
 {

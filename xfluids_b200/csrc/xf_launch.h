@@ -19,9 +19,9 @@ struct XfTma
 		int launch_rk_prim(const XfDev &d, const XfThermo &th, int ns, int cop, double *U, double *U1, const double *dt_dev, int flag, int guard, int nflags, \
 						   cudaStream_t s, long long *launches);                                                            \
 		int launch_sweeps(const XfDev &d, int ns, int cop, const double *U, cudaStream_t s, long long *launches, int dirmask, int kp0, int kp1, int tz0, int tz1, \
-						  const CUtensorMap *tmy, const CUtensorMap *tmz);                                                      \
+						  const CUtensorMap *tmy, const CUtensorMap *tmz, const XfViscF *vf);                                   \
 		int xf_z_tiles(const XfDev &d);                                                                                       \
-		int launch_visc(const XfDev &d, const XfThermo &th, const XfVisc &vs, int ns, int cop, const double *U, const int bc[6], cudaStream_t s, long long *launches); \
+		int launch_visc(const XfDev &d, const XfThermo &th, const XfVisc &vs, int ns, int cop, const double *U, const int bc[6], cudaStream_t s, long long *launches, int parts); \
 		int launch_sweep_x(const XfDev &d, int ns, int cop, const double *U, const XfMarchArgs &a, cudaStream_t s);           \
 		int launch_march(const XfDev &d, int ns, int cop, const XfTma &tm, const double *UI, const XfMarchArgs &a, int dir, cudaStream_t s); \
 		int z_tile_faces();                                                                                                   \

@@ -90,6 +90,19 @@ struct XfVisc
 	double *lim;   // device doubles: [0..NS) yi_min, [NS..2NS) yi_max -> after k_visc_limits: [2NS..3NS) Yil_limiter, [3NS..4NS) Diffu_limiter
 };
 
+// what the wall-flux part of the viscous block reads (the tail of a sweep carries it by value)
+struct XfViscF
+{
+	int heat, diffu;
+	const double *Vde, *va, *tca, *Dkm, *hi, *lim;
+};
+static inline XfViscF xf_visc_face_args(const XfVisc &v)
+{
+	XfViscF f;
+	f.heat = v.heat, f.diffu = v.diffu, f.Vde = v.Vde, f.va = v.va, f.tca = v.tca, f.Dkm = v.Dkm, f.hi = v.hi, f.lim = v.lim;
+	return f;
+}
+
 // Cells no ghost fill / halo pack reads: at least one more ghost width away from every face of the inner block.  The stage update can go
 // straight on to their primitive recovery (k_rk_prim); the shell around them waits for the ghost fill (k_prim_shell).  GhostSpecies
 // renormalisation rewrites U, so a cell must be recovered exactly once per stage and only after every reader of its raw update is done.

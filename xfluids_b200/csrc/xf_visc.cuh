@@ -121,14 +121,16 @@ __global__ void __launch_bounds__(256) k_vde_bc(XfDev d, XfVisc vs, int bc_min, 
 }
 
 // ln(coefficient) = ((c3 L + c2) L + c1) L + c0 with L = ln T  (Viscosity / Thermal_conductivity / GetDkj, Visc_device.h:10-101)
-static __device__ __noinline__ double xf_pow_half(double x) { return xf_pow(x, 0.5); }
-// (out of line: thirty inlined copies of exp() made k_transport stall on instruction fetch)
-static __device__ __noinline__ double xf_fit4(double c0, double c1, double c2, double c3, double L) { return xf_exp(((c3 * L + c2) * L + c1) * L + c0); } // glibc's exp, bit for bit (xf_exp.cuh)
-#define xf_fit(c, L) xf_fit4((c)[0], (c)[1], (c)[2], (c)[3], (L)) // by value: the coefficients live in the kernel-parameter bank
+// Out of line (thirty inlined copies of exp() made k_transport stall on instruction fetch) and two arguments per call: exp and pow are
+// single dependency chains of ~15 / ~40 FP64 instructions, two independent ones interleave in the FP64 pipe (the kernel's top stall was
+// `wait`).  glibc's exp / pow, bit for bit (xf_exp.cuh).
+static __device__ __noinline__ double2 xf_exp_pair(double a, double b) { return make_double2(xf_exp(a), xf_exp(b)); }
+static __device__ __noinline__ double2 xf_pow_half_pair(double a, double b) { return make_double2(xf_pow(a, 0.5), xf_pow(b, 0.5)); }
+#define xf_fit_arg(c, L) ((((c)[3] * (L) + (c)[2]) * (L) + (c)[1]) * (L) + (c)[0]) // by value: the coefficients live in the kernel-parameter bank
 
 // Gettransport_coeff_aver over ALL cells (Visc_kernels.hpp:219-241)
 template <class C>
-__global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc vs, const double *__restrict__ U, int k0, int k1)
+__global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVisc vs, const double *__restrict__ U, int k0, int k1)
 {
 	constexpr int NS = C::NS;
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,22 +180,41 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 	double mu[NS], lam[NS];
 #pragma unroll
 	for (int n = 0; n < NS; n++)
-		mu[n] = xf_fit(vs.fit_visc[n], L), lam[n] = vs.heat ? xf_fit(vs.fit_therm[n], L) : 0.0;
+	{
+		const double2 e = xf_exp_pair(xf_fit_arg(vs.fit_visc[n], L), vs.heat ? xf_fit_arg(vs.fit_therm[n], L) : 0.0);
+		mu[n] = e.x, lam[n] = vs.heat ? e.y : 0.0;
+	}
+	// quotients by one denominator share its IEEE reciprocal (xf_div_shared, xf_math.cuh: the correctly rounded quotient in 3 instructions)
+	const double sqrt2 = sqrt(2.0), _sqrt2 = 1.0 / sqrt2, _p = 1.0 / p;
+	// den_k = sum_i X_i PHI(k, i), i ascending (Visc_device.h:34-41, 120-140).  The two PHI of an unordered pair are evaluated together; the
+	// loop order below still adds the terms of every den_k in ascending i: (j, k) pairs with j < k arrive at outer index j, the diagonal
+	// term at the start of outer index k, the (k, i > k) terms after it.
+	double den[NS];
+#pragma unroll
+	for (int n = 0; n < NS; n++)
+		den[n] = 0.0;
+	auto phi_of = [&](int kk, int ii, double root) { // root = pow(mu_k / mu_i, 0.5)
+		double phi = vs.phiW[kk * NS + ii] * root;
+		phi = xf_div_shared((phi + 1.0) * (phi + 1.0) * 0.5, sqrt2, _sqrt2);
+		return phi * vs.phiS[kk * NS + ii];
+	};
+#pragma unroll
+	for (int a = 0; a < NS; a++)
+	{
+		den[a] = den[a] + X[a] * phi_of(a, a, 1.0); // pow(1, 0.5) == 1
+#pragma unroll
+		for (int b = a + 1; b < NS; b++)
+		{
+			const double2 r = xf_pow_half_pair(mu[a] / mu[b], mu[b] / mu[a]);
+			den[a] = den[a] + X[b] * phi_of(a, b, r.x);
+			den[b] = den[b] + X[a] * phi_of(b, a, r.y);
+		}
+	}
 	double va = 0.0, tca = 0.0;
-	const double sqrt2 = sqrt(2.0);
 #pragma unroll
 	for (int kk = 0; kk < NS; kk++)
 	{
-		double den = 0.0;
-#pragma unroll
-		for (int ii = 0; ii < NS; ii++)
-		{ // PHI(specie_k, specie_i) (Visc_device.h:34-41)
-			double phi = vs.phiW[kk * NS + ii] * (ii == kk ? 1.0 : xf_pow_half(mu[kk] / mu[ii])); // pow(1, 0.5) == 1
-			phi = (phi + 1.0) * (phi + 1.0) * 0.5 / sqrt2;
-			phi = phi * vs.phiS[kk * NS + ii];
-			den = den + X[ii] * phi;
-		}
-		const double _den = 1.0 / den;
+		const double _den = 1.0 / den[kk];
 		va = va + X[kk] * mu[kk] * _den;
 		if (vs.heat)
 			tca = tca + X[kk] * lam[kk] * _den;
@@ -206,19 +227,43 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 		double Dk[NS];
 		if constexpr (NS > 1)
 		{
-			// (X_i + 1e-40) / (D_ik / p + 1e-40) per ordered pair; with bitwise symmetric fits (GetFitCoefficient's are) D_ik is D_ki
+			// (X_i + 1e-40) / (D_ik / p + 1e-40) per ordered pair; with bitwise symmetric fits (GetFitCoefficient's are) D_ik is D_ki and the
+			// NS (NS - 1) / 2 coefficients of the upper triangle are evaluated two per call
+			constexpr int NP = NS * (NS - 1) / 2;
 			double Dp[NS][NS];
+			for (int pass = 0; pass < (vs.dkj_sym ? 1 : 2); pass++)
+			{
+				double arg[NP + 1];
+				{
+					int q = 0;
 #pragma unroll
-			for (int kk = 0; kk < NS; kk++)
+					for (int kk = 0; kk < NS; kk++)
 #pragma unroll
-				for (int ii = 0; ii < NS; ii++)
-					if (ii != kk)
-					{
-						if (ii > kk || !vs.dkj_sym)
-							Dp[kk][ii] = xf_fit(vs.fit_Dkj[ii * NS + kk], L) / p + 1.0e-40;
-						else
-							Dp[kk][ii] = Dp[ii][kk];
-					}
+						for (int ii = kk + 1; ii < NS; ii++, q++)
+							arg[q] = pass == 0 ? xf_fit_arg(vs.fit_Dkj[ii * NS + kk], L) : xf_fit_arg(vs.fit_Dkj[kk * NS + ii], L);
+					arg[NP] = 0.0;
+				}
+#pragma unroll
+				for (int q = 0; q < NP; q += 2)
+				{
+					const double2 e = xf_exp_pair(arg[q], arg[q + 1]);
+					arg[q] = e.x, arg[q + 1] = e.y;
+				}
+				{
+					int q = 0;
+#pragma unroll
+					for (int kk = 0; kk < NS; kk++)
+#pragma unroll
+						for (int ii = kk + 1; ii < NS; ii++, q++)
+						{
+							const double v = xf_div_shared(arg[q], p, _p) + 1.0e-40;
+							if (pass == 0)
+								Dp[kk][ii] = v, Dp[ii][kk] = v; // Dp[kk][ii] uses fit_Dkj[ii * NS + kk]; symmetric: the same for [ii][kk]
+							else
+								Dp[ii][kk] = v;                 // not symmetric: Dp[ii][kk] uses fit_Dkj[kk * NS + ii]
+						}
+				}
+			}
 #pragma unroll
 			for (int kk = 0; kk < NS; kk++)
 			{
@@ -232,7 +277,7 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 					}
 				// sycl::step(ceil(temp1), 0.0) == 1 <=> 0.0 >= ceil(temp1)
 				if (!(0.0 < ceil(temp1)))
-					Dk[kk] = xf_fit(vs.fit_Dkj[kk * NS + kk], L) / p;
+					Dk[kk] = xf_exp(xf_fit_arg(vs.fit_Dkj[kk * NS + kk], L)) / p;
 				else
 					Dk[kk] = temp1 / temp2 / rho * C_total;
 				Dk[kk] *= 1.0e-1;
@@ -240,7 +285,7 @@ __global__ void __launch_bounds__(128) k_transport(XfDev d, XfThermo th, XfVisc 
 		}
 		else
 		{
-			Dk[0] = xf_fit(vs.fit_Dkj[0], L) / p;
+			Dk[0] = xf_exp(xf_fit_arg(vs.fit_Dkj[0], L)) / p;
 			Dk[0] *= 1.0e-1;
 		}
 #pragma unroll
@@ -309,98 +354,15 @@ __global__ void k_visc_limits(XfVisc vs, int NS)
 	vs.lim[2 * NS + n] = ymax, vs.lim[3 * NS + n] = dmax;
 }
 
-// GetWallViscousFlux{X,Y,Z}: Flux_wall -= F_wall_v at the face of direction DIR above cell id
+// GetWallViscousFlux{X,Y,Z}: Flux_wall -= F_wall_v at the face of direction DIR above cell id (the flux itself: xf_visc_face.cuh)
 template <class C, int DIR>
 __device__ __forceinline__ void visc_face(const XfDev &d, const XfVisc &vs, const double *__restrict__ U, double *__restrict__ Fw, const long long id)
 {
-	constexpr int NS = C::NS, E = C::E;
-	const long long s = DIR == 0 ? 1 : (DIR == 1 ? d.sY : d.sZ);
-	const long long id_m1 = id - s, id_p1 = id + s, id_p2 = id + 2 * s;
-	const double _sxtn = 1.0 / 16.0, _twfr = 1.0 / 24.0, _OT = 1.0 / 3.0;
-	const double _dl = DIR == 0 ? d._dx : (DIR == 1 ? d._dy : d._dz);
-	const double tX = d.DimX ? 1.0 : 0.0, tY = d.DimY ? 1.0 : 0.0, tZ = d.DimZ ? 1.0 : 0.0;
-	auto avg = [&](const double *q) { return (9.0 * (q[id_p1] + q[id]) - (q[id_p2] + q[id_m1])) * _sxtn; };
-	auto grad = [&](const double *q) { return (27.0 * (q[id_p1] - q[id]) - (q[id_p2] - q[id_m1])) * _dl * _twfr; };
-	const double *Vd = vs.Vde;
-	const long long N = d.N;
-	const double mue = avg(vs.va);
-	const double lamada = -2.0 * _OT * mue;
-	double f_x, f_y, f_z, u_hlf, v_hlf, w_hlf;
-	if constexpr (DIR == 0)
-	{ // Ducy 3, Ducz 6, Dvcy 4, Dwcz 8
-		f_x = (2.0 * mue + lamada) * (27.0 * (d.u[id_p1] - d.u[id]) - (d.u[id_p2] - d.u[id_m1])) * _dl * _twfr;
-		f_x += lamada * (9.0 * (Vd[4 * N + id_p1] + Vd[4 * N + id]) - (Vd[4 * N + id_p2] + Vd[4 * N + id_m1]) + 9.0 * (Vd[8 * N + id_p1] + Vd[8 * N + id]) - (Vd[8 * N + id_p2] + Vd[8 * N + id_m1])) * _sxtn;
-		f_y = mue * (27.0 * (d.v[id_p1] - d.v[id]) - (d.v[id_p2] - d.v[id_m1])) * _dl * _twfr * tY;
-		f_y += mue * (9.0 * (Vd[3 * N + id_p1] + Vd[3 * N + id]) - (Vd[3 * N + id_p2] + Vd[3 * N + id_m1])) * _sxtn * tY;
-		f_z = mue * (27.0 * (d.w[id_p1] - d.w[id]) - (d.w[id_p2] - d.w[id_m1])) * _dl * _twfr * tZ;
-		f_z += mue * (9.0 * (Vd[6 * N + id_p1] + Vd[6 * N + id]) - (Vd[6 * N + id_p2] + Vd[6 * N + id_m1])) * _sxtn * tZ;
-		u_hlf = avg(d.u), v_hlf = avg(d.v) * tY, w_hlf = avg(d.w) * tZ;
-	}
-	else if constexpr (DIR == 1)
-	{ // Dvcx 1, Dvcz 7, Ducx 0, Dwcz 8
-		f_x = mue * (27.0 * (d.u[id_p1] - d.u[id]) - (d.u[id_p2] - d.u[id_m1])) * _dl * _twfr * tX;
-		f_x += mue * (9.0 * (Vd[1 * N + id_p1] + Vd[1 * N + id]) - (Vd[1 * N + id_p2] + Vd[1 * N + id_m1])) * _sxtn * tX;
-		f_y = (2.0 * mue + lamada) * (27.0 * (d.v[id_p1] - d.v[id]) - (d.v[id_p2] - d.v[id_m1])) * _dl * _twfr;
-		f_y += lamada * (9.0 * (Vd[0 * N + id_p1] + Vd[0 * N + id]) - (Vd[0 * N + id_p2] + Vd[0 * N + id_m1]) + 9.0 * (Vd[8 * N + id_p1] + Vd[8 * N + id]) - (Vd[8 * N + id_p2] + Vd[8 * N + id_m1])) * _sxtn;
-		f_z = mue * (27.0 * (d.w[id_p1] - d.w[id]) - (d.w[id_p2] - d.w[id_m1])) * _dl * _twfr * tZ;
-		f_z += mue * (9.0 * (Vd[7 * N + id_p1] + Vd[7 * N + id]) - (Vd[7 * N + id_p2] + Vd[7 * N + id_m1])) * _sxtn * tZ;
-		u_hlf = avg(d.u) * tX, v_hlf = avg(d.v), w_hlf = avg(d.w) * tZ;
-	}
-	else
-	{ // Dwcx 2, Dwcy 5, Ducx 0, Dvcy 4
-		f_x = mue * (27.0 * (d.u[id_p1] - d.u[id]) - (d.u[id_p2] - d.u[id_m1])) * _dl * _twfr * tX;
-		f_x += mue * (9.0 * (Vd[2 * N + id_p1] + Vd[2 * N + id]) - (Vd[2 * N + id_p2] + Vd[2 * N + id_m1])) * _sxtn * tX;
-		f_y = mue * (27.0 * (d.v[id_p1] - d.v[id]) - (d.v[id_p2] - d.v[id_m1])) * _dl * _twfr * tY;
-		f_y += mue * (9.0 * (Vd[5 * N + id_p1] + Vd[5 * N + id]) - (Vd[5 * N + id_p2] + Vd[5 * N + id_m1])) * _sxtn * tY;
-		f_z = (2.0 * mue + lamada) * (27.0 * (d.w[id_p1] - d.w[id]) - (d.w[id_p2] - d.w[id_m1])) * _dl * _twfr;
-		f_z += lamada * (9.0 * (Vd[0 * N + id_p1] + Vd[0 * N + id]) - (Vd[0 * N + id_p2] + Vd[0 * N + id_m1]) + 9.0 * (Vd[4 * N + id_p1] + Vd[4 * N + id]) - (Vd[4 * N + id_p2] + Vd[4 * N + id_m1])) * _sxtn;
-		u_hlf = avg(d.u) * tX, v_hlf = avg(d.v) * tY, w_hlf = avg(d.w);
-	}
-	double Fv[E];
-	Fv[0] = 0.0, Fv[1] = f_x, Fv[2] = f_y, Fv[3] = f_z;
-	Fv[4] = f_x * u_hlf + f_y * v_hlf + f_z * w_hlf;
-	if (vs.heat)
-	{ // MARCO_VIS_HEAT
-		double kk_ = avg(vs.tca);
-		kk_ *= grad(d.T);
-		Fv[4] += kk_;
-	}
-	if (vs.diffu)
-	{ // MARCO_VIS_Diffu
-		const double rho_wall = avg(U);
-		double CorrectTerm = 0.0, Dim_Yil = 1.0E-20;
-		double Yi_wall[NS];
+	double Fv[C::E];
+	visc_face_flux<C, DIR>(d, vs, U, id, Fv);
 #pragma unroll
-		for (int l = 0; l < NS; l++)
-		{
-			const double hi_wall = avg(vs.hi + l * N), Dim_wall = avg(vs.Dkm + l * N);
-			double Yil_wall = 0.0;
-			if constexpr (C::COP)
-			{
-				const double *Y = d.y + l * N;
-				const double yl = vs.lim[2 * NS + l], dlm = vs.lim[3 * NS + l];
-				Yil_wall = xf_min(xf_max(grad(Y), -yl), yl);
-				Yi_wall[l] = xf_min(xf_max(avg(Y), 1.0E-20), 1.0);
-				Dim_Yil = xf_min(xf_max(Dim_wall * Yil_wall, -dlm), dlm);
-				CorrectTerm += Dim_Yil;
-			}
-			(void)Yil_wall;
-			Fv[4] += rho_wall * hi_wall * Dim_Yil;
-		}
-		CorrectTerm *= rho_wall;
-#pragma unroll
-		for (int p = 5; p < E; p++)
-			Fv[p] = rho_wall * Dim_Yil - Yi_wall[p - 5] * CorrectTerm;
-	}
-	else
-	{
-#pragma unroll
-		for (int p = 5; p < E; p++)
-			Fv[p] = 0.0;
-	}
-#pragma unroll
-	for (int n = 0; n < E; n++)
-		Fw[n * N + id] -= Fv[n];
+	for (int n = 0; n < C::E; n++)
+		Fw[n * d.N + id] -= Fv[n];
 }
 
 // All three directions in one pass: one thread per cell of the box [B - 1, B + inner) of every active direction forms the viscous flux at
@@ -434,8 +396,12 @@ __global__ void __launch_bounds__(128) k_visc_flux3(XfDev d, XfVisc vs, const do
 
 // the viscous block of GetLU (ConVenction_block.hpp:424-575) after the inviscid wall fluxes (and their limiter) are in Fw; U = the sweep input
 template <class C>
-static int visc_t(const XfDev &d, const XfThermo &th, const XfVisc &vs, const double *U, const int bc[6], cudaStream_t s, long long *launches)
+// parts: 1 = everything the wall fluxes read (derivatives + their ghost fill, transport coefficients, limiter extrema), 2 = the wall fluxes
+// (stand-alone kernel; the sweeps' tails do the same on the fly), 3 = both
+static int visc_t(const XfDev &d, const XfThermo &th, const XfVisc &vs, const double *U, const int bc[6], cudaStream_t s, long long *launches, int parts)
 {
+	if (parts & 1)
+	{
 	const long long nv = (long long)(d.DimX ? d.Xi + 4 : 1) * (d.DimY ? d.Yi + 4 : 1) * (d.DimZ ? d.Zi + 4 : 1);
 	k_vde<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(d, vs);
 	++*launches;
@@ -456,6 +422,8 @@ static int visc_t(const XfDev &d, const XfThermo &th, const XfVisc &vs, const do
 		k_visc_limits<<<1, 32, 0, s>>>(vs, C::NS);
 		*launches += 2;
 	}
+	}
+	if (parts & 2)
 	{
 		constexpr int TT = XF_RK_TILE > 0 ? XF_RK_TILE : 8;
 		const int nx = d.Xi + (d.DimX ? 1 : 0), ny = d.Yi + (d.DimY ? 1 : 0), nz = d.Zi + (d.DimZ ? 1 : 0);
