@@ -150,6 +150,10 @@ int xf_clear_errors(xf_ctx *ctx);
  * the 3 directional dt maxima (double[3]) and the error word (int[4]). */
 double *xf_device_dtmax(xf_ctx *ctx);
 int *xf_device_errors(xf_ctx *ctx);
+/* 1 when the species-diffusion limiter of the viscous block reads domain-wide extrema of the mass fractions (xf_transport.dim_max0 != 0, the
+ * reference's MPI build: ConVenction_block.hpp:489-503 MPI-reduces yi_min / yi_max); the built-in slab driver refuses such a setup on N > 1 ranks
+ * instead of limiting with per-slab extrema */
+int xf_transport_needs_global_extrema(const xf_ctx *ctx);
 double *xf_device_glfmax(xf_ctx *ctx);   /* 9 device doubles: the GLF running maxima of |lambda| (dir*3 + {u-c, u, u+c}), eigen_block_{x,y,z} of ConVenction_block.hpp:115-215 */
 
 /* ---- z-slab halo (replaces FluidMpiCopyKernelZ pack/unpack, src/solver_BCs/BCs_kernels.hpp:304-324 and

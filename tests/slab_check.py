@@ -53,10 +53,12 @@ def main():
     ap.add_argument("--weno", type=int, default=5)
     ap.add_argument("--pp", type=int, default=0, help="positivity-preserving limiter on, at CFL 0.9 (where it acts)")
     ap.add_argument("--alpha", default="LLF", help="LLF | ROE | GLF (GLF: 9 running maxima MAX-reduced over the ranks every stage)")
+    ap.add_argument("--visc", action="store_true", help="viscous / heat-conduction / species-diffusion terms on (the slabs' split stages run the stand-alone wall-flux "
+                    "kernel after the z halo has arrived, the undecomposed block the sweeps' viscous tails)")
     ap.add_argument("--periodic-z", action="store_true", help="periodic z boundary: the outer faces of the first / last rank exchange with each other (on 2 ranks both neighbours are the same peer)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    extra = ["-weno=%d" % a.weno, "-alpha=" + a.alpha] + (["-pp=1", "-cfl=0.9"] if a.pp else [])
+    extra = ["-weno=%d" % a.weno, "-alpha=" + a.alpha] + (["-pp=1", "-cfl=0.9"] if a.pp else []) + (["-visc=1"] if a.visc else [])
     if a.periodic_z:
         js, _, _ = CASES[a.case]
         bc0 = host.Setup(os.path.join(REPO, "settings", js), []).bc
@@ -124,6 +126,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     for overlap in (False, True):
         eng = capi.Engine(mine.block, mine.thermal, mine.scheme, device=local, keepalive=(mine,))
+        if a.visc:
+            eng.set_transport(mine.transport, keepalive=(mine,))
         eng.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             eng.set_state(Um, Tm)
@@ -141,10 +145,12 @@ def main():
         eng.close()
     assert np.array_equal(results[False][0], results[True][0]), "overlapped exchange changed the result"
     # host-buffer step (bench e2e on N > 1): the chunked, overlapped form against upload -> step -> download, 2 steps each
-    if a.alpha != "GLF":
+    if a.alpha != "GLF" and not a.visc:   # (the chunked host step is switched off with the viscous terms on)
         hres = {}
         for mode in ("plain", "overlapped"):
             eng = capi.Engine(mine.block, mine.thermal, mine.scheme, device=local, keepalive=(mine,))
+            if a.visc:
+                eng.set_transport(mine.transport, keepalive=(mine,))
             eng.set_stream(stream.cuda_stream)
             eng.L.check(eng.L.dll.xf_set_host_overlap(eng.ctx, 4))
             with torch.cuda.stream(stream):
@@ -174,6 +180,8 @@ def main():
     dist.all_gather_object(gathered, (mineU[Bz:Bz + zi], tmine))
     if rank == 0:
         eng = capi.Engine(one.block, one.thermal, one.scheme, device=local, keepalive=(one,))
+        if a.visc:
+            eng.set_transport(one.transport, keepalive=(one,))
         eng.set_state(U1, T1)
         eng.boundary(eng.U, one.bc)
         assert eng.update_states(eng.U) == 0

@@ -45,11 +45,12 @@ def test_exchange_protocol_periodic_z_gloo(world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,strong,weno,pp,alpha", [("sbi", False, 5, 0, "LLF"), ("jet", True, 5, 0, "LLF"), ("sbi", False, 6, 1, "LLF"), ("sbi", False, 7, 0, "ROE"),
-                                                       ("sbi", False, 5, 0, "GLF"), ("jet", True, 6, 0, "GLF"), ("sbi-periodic", False, 5, 0, "LLF")])
+                                                       ("sbi", False, 5, 0, "GLF"), ("jet", True, 6, 0, "GLF"), ("sbi-periodic", False, 5, 0, "LLF"),
+                                                       ("sbi-visc", False, 5, 0, "LLF"), ("jet-visc", True, 6, 1, "GLF")])
 def test_two_slabs_equal_one_block_bitwise(case, strong, weno, pp, alpha):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    per = case.endswith("-periodic")
+    per, visc = case.endswith("-periodic"), case.endswith("-visc")
     _launch(2, ["--mode", "gpu", "--case", case.split("-")[0], "--steps", "5", "--weno", str(weno), "--pp", str(pp), "--alpha", alpha] + (["--strong"] if strong else [])
-            + (["--periodic-z"] if per else []))
+            + (["--periodic-z"] if per else []) + (["--visc"] if visc else []))

@@ -46,6 +46,7 @@ _PROTOS = {
     "xf_destroy": (C.c_int, [_P]),
     "xf_last_error": (C.c_char_p, []),
     "xf_set_transport": (C.c_int, [_P, C.POINTER(XfTransport)]),
+    "xf_transport_needs_global_extrema": (C.c_int, [_P]),
     "xf_set_stream": (C.c_int, [_P, _P]),
     "xf_synchronize": (C.c_int, [_P]),
     "xf_pitch": (C.c_size_t, [_P]),

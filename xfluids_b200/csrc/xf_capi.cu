@@ -609,6 +609,10 @@ extern "C"
 		return ensure_fw(c);
 	}
 
+	// 1 when the species-diffusion limiter depends on domain-wide extrema of the mass fractions (Dim_max != 0: the reference's MPI build,
+	// ConVenction_block.hpp:489-503 reduces them over the ranks); a slab driver would have to MIN / MAX-reduce them every stage
+	int xf_transport_needs_global_extrema(const xf_ctx *c) { return (c && c->vs.on && c->vs.diffu && c->vs.dim_max0 != 0.0) ? 1 : 0; }
+
 	// ---- TMA tensor maps of the marching sweeps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
 	typedef CUresult (*xf_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
 									 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

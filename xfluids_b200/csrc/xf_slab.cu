@@ -308,6 +308,8 @@ extern "C"
 	{
 		if (flag < 1 || flag > 3)
 			return sfail(XF_ERR_ARG, "flag must be 1..3");
+		if ((s->lo >= 0 || s->hi >= 0) && xf_transport_needs_global_extrema(s->c))
+			return sfail(XF_ERR_ARG, "species-diffusion limiter with domain-wide mass-fraction extrema (-diffu-mpi) is not reduced over the slabs: single GPU only");
 		double *UI = flag == 1 ? U : U1;
 		int rc;
 		XS(xf_boundary(s->c, UI, s->bc));
