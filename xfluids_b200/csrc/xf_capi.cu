@@ -1123,9 +1123,22 @@ extern "C"
 	{
 		CU(cudaSetDevice(c->device));
 		const int NE = 1 + 3 * 6 + 1;
-		cudaEvent_t ev[NE];
+		struct Events
+		{ // destroyed on every exit path
+			cudaEvent_t ev[NE];
+			int n = 0;
+			~Events()
+			{
+				for (int i = 0; i < n; i++)
+					cudaEventDestroy(ev[i]);
+			}
+		} evs;
+		cudaEvent_t *ev = evs.ev;
 		for (int i = 0; i < NE; i++)
+		{
 			CU(cudaEventCreate(&ev[i]));
+			evs.n = i + 1;
+		}
 		int e = 0, rc;
 		const bool fuse = can_fuse(c);
 		CU(cudaEventRecord(ev[e++], c->stream));
@@ -1184,8 +1197,6 @@ extern "C"
 			}
 		CU(cudaEventElapsedTime(&t, ev[0], ev[NE - 1]));
 		ms[7] = t;
-		for (int i = 0; i < NE; i++)
-			cudaEventDestroy(ev[i]);
 		return XF_OK;
 	}
 
