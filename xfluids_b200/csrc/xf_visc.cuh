@@ -189,10 +189,10 @@ __global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVi
 	// den_k = sum_i X_i PHI(k, i), i ascending (Visc_device.h:34-41, 120-140).  The two PHI of an unordered pair are evaluated together; the
 	// loop order below still adds the terms of every den_k in ascending i: (j, k) pairs with j < k arrive at outer index j, the diagonal
 	// term at the start of outer index k, the (k, i > k) terms after it.
-	double den[NS];
+	double den[NS], _mu[NS];
 #pragma unroll
 	for (int n = 0; n < NS; n++)
-		den[n] = 0.0;
+		den[n] = 0.0, _mu[n] = 1.0 / mu[n]; // every mu_n is the denominator of NS - 1 ratios
 	auto phi_of = [&](int kk, int ii, double root) { // root = pow(mu_k / mu_i, 0.5)
 		double phi = vs.phiW[kk * NS + ii] * root;
 		phi = xf_div_shared((phi + 1.0) * (phi + 1.0) * 0.5, sqrt2, _sqrt2);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVi
 #pragma unroll
 		for (int b = a + 1; b < NS; b++)
 		{
-			const double2 r = xf_pow_half_pair(mu[a] / mu[b], mu[b] / mu[a]);
+			const double2 r = xf_pow_half_pair(xf_div_shared(mu[a], mu[b], _mu[b]), xf_div_shared(mu[b], mu[a], _mu[a]));
 			den[a] = den[a] + X[b] * phi_of(a, b, r.x);
 			den[b] = den[b] + X[a] * phi_of(b, a, r.y);
 		}
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVi
 			// (X_i + 1e-40) / (D_ik / p + 1e-40) per ordered pair; with bitwise symmetric fits (GetFitCoefficient's are) D_ik is D_ki and the
 			// NS (NS - 1) / 2 coefficients of the upper triangle are evaluated two per call
 			constexpr int NP = NS * (NS - 1) / 2;
-			double Dp[NS][NS];
+			double Dp[NS][NS], _Dp[NS][NS]; // D_ik / p + 1e-40 and its reciprocal (symmetric fits: one reciprocal serves both quotients of a pair)
 			for (int pass = 0; pass < (vs.dkj_sym ? 1 : 2); pass++)
 			{
 				double arg[NP + 1];
@@ -257,10 +257,11 @@ __global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVi
 						for (int ii = kk + 1; ii < NS; ii++, q++)
 						{
 							const double v = xf_div_shared(arg[q], p, _p) + 1.0e-40;
+							const double _v = 1.0 / v;
 							if (pass == 0)
-								Dp[kk][ii] = v, Dp[ii][kk] = v; // Dp[kk][ii] uses fit_Dkj[ii * NS + kk]; symmetric: the same for [ii][kk]
+								Dp[kk][ii] = v, Dp[ii][kk] = v, _Dp[kk][ii] = _v, _Dp[ii][kk] = _v; // Dp[kk][ii] uses fit_Dkj[ii * NS + kk]; symmetric: the same for [ii][kk]
 							else
-								Dp[ii][kk] = v;                 // not symmetric: Dp[ii][kk] uses fit_Dkj[kk * NS + ii]
+								Dp[ii][kk] = v, _Dp[ii][kk] = _v; // not symmetric: Dp[ii][kk] uses fit_Dkj[kk * NS + ii]
 						}
 				}
 			}
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(128, 5) k_transport(XfDev d, XfThermo th, XfVi
 					if (ii != kk)
 					{
 						temp1 += (X[ii] + 1.0e-40) * vs.Wi[ii];
-						temp2 += (X[ii] + 1.0e-40) / Dp[kk][ii];
+						temp2 += xf_div_shared(X[ii] + 1.0e-40, Dp[kk][ii], _Dp[kk][ii]);
 					}
 				// sycl::step(ceil(temp1), 0.0) == 1 <=> 0.0 >= ceil(temp1)
 				if (!(0.0 < ceil(temp1)))
