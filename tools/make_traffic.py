@@ -21,6 +21,7 @@ WORKLOADS = {  # summary file tag -> (traffic.json key, faces per sweep launch b
     "w7": ("sbi:512x512x512:weno7", {"x": 513 * 512 * 512, "y": 512 * 513 * 512, "z": 512 * 512 * 513}),
     "riemann": ("riemann:4096x4096x1:weno5", {"x": 4097 * 4096, "y": 4096 * 4097}),
     "vortex": ("vortex:1024x1024x1:weno5", {"x": 1025 * 1024, "y": 1024 * 1025}),
+    "visc": ("sbi:512x512x512:weno5:visc", {"x": 513 * 512 * 512, "y": 512 * 513 * 512, "z": 512 * 512 * 513}),
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 

@@ -1,16 +1,20 @@
-// xf_kernels.cu -- hand-written sm_100a kernels of the inviscid RHS path.  Compiled twice:
+// xf_kernels.cu -- hand-written sm_100a kernels of the per-stage right-hand side.  Compiled twice:
 //   -DXF_NS=xf_strict -fmad=false   (parity mode: no FMA contraction)
 //   -DXF_NS=xf_fast   -fmad=true    (same formulas, contraction allowed)
-// Kernels (one launch each unless noted):
-//   k_prim      cons->prim + Newton T + per-cell pressure derivatives (+ dt / GLF maxima, guards)   a3,a4,a5,a1,a6',a10
-//   k_sweep     characteristic WENO flux at the faces of one direction, stencil staged in shared memory  a6,a7
-//   k_lu        flux divergence                                                                        a8
-//   k_rk        SSP-RK3 stage update (+ U/LU NaN guard)                                                a9,a10
-//   k_lu_rk     k_lu + k_rk fused (fast path: LU never touches HBM)
-//   k_bc        ghost-cell fill, one launch per direction                                             a2
-//   k_dt        stand-alone CFL maxima (API parity with GetDt)                                        a1
-//   k_dt_final  dt = CFL/sum, clip to t_end, advance device time
-//   k_aos2soa / k_soa2aos / k_halo_pack / k_halo_unpack   layout + z-slab halo
+// Kernels (one launch each unless noted; a<n> = the SURVEY 8(a) function rows they cover):
+//   k_prim, k_prim_hard   cons->prim + Newton T + per-cell pressure derivatives (+ dt / GLF maxima, guards)            a3,a4,a5,a1,a6',a10
+//   k_prim_shell          the same for the cells around the deep block (opt-in update -> recovery fusion)
+//   k_sweep<.., PP, ACC, VISC>  characteristic WENO flux at the faces of one direction, stencil staged in shared memory (the conserved
+//                         pencil of a y / z tile by one TMA bulk-tensor copy), limiter and viscous wall flux in the tail        a6,a7 (+ f1, f3)
+//   k_lu                  flux divergence (block-level API)                                                                    a8
+//   k_rk<E, fused>        flux divergence + NaN guard + SSP-RK3 stage update: LU never touches HBM on the fused path           a8,a9,a10
+//   k_rk_prim             k_rk going straight on to the next stage's primitive recovery (opt-in, XF_FUSE_PRIM=1)
+//   k_march               TMA-fed marching y / z sweep with divergence / update fused in (xf_march.cuh; opt-in, XF_MARCH=1)
+//   k_vde, k_vde_bc, k_transport, k_yi_minmax, k_visc_limits, k_visc_flux3   viscous block (xf_visc.cuh)                        f3
+//   k_bc                  ghost-cell fill, one launch per direction                                                            a2
+//   k_dt                  stand-alone CFL maxima (API parity with GetDt)                                                       a1
+//   k_dt_final            dt = CFL/sum, clip to t_end, advance device time
+//   k_layout / k_scalar_pad / k_halo   AoS <-> SoA at the boundary, z-slab halo pack / unpack
 #include <cuda_runtime.h>
 #include <cstdio>
 #include "xf_math.cuh"
@@ -774,7 +778,7 @@ __global__ void __launch_bounds__(DIR == 0 ? XfTx<WENO, PP>::V : XF_TW * XF_TF, 
 
 // ---------------------------------------------------------------------------------------------
 // k_lu: UpdateFluidLU (Reconstruction_kernels.hpp:201-234); k_rk: UpdateURK3rdKernel (Update_kernels.hpp:64-94) with
-// EstimateFluidNANKernel (Fluids.cpp:47-87) folded in; k_lu_rk: both, LU kept in registers.
+// EstimateFluidNANKernel (Fluids.cpp:47-87) folded in; k_rk<E, true>: both, LU kept in registers.
 // One thread per inner cell, x fastest.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool inner_cell(const XfDev &d, long long &id)
