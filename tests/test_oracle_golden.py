@@ -80,7 +80,7 @@ def test_oracle_matches_reference_golden_cu6_and_positivity(case, weno, pp):
     assert not o.flags().any()
 
 
-VISC_FIXTURES = ["sbi_w5_visc", "jet_w5_visc", "sbi_w6_glf_pp_visc"]
+VISC_FIXTURES = ["sbi_w5_visc", "jet_w5_visc", "sbi_w6_glf_pp_visc", "sbi_w5_visc2d"]
 
 
 @pytest.mark.parametrize("name", VISC_FIXTURES)
