@@ -115,3 +115,35 @@ def test_viscous_steps_vs_reference_golden(name):
         tref += float(d)
     assert t == tref
     eng.close()
+
+
+@pytest.mark.gpu
+def test_species_diffusion_with_the_mpi_builds_limiter_equals_oracle():
+    """With Dim_max = 0 (the reference's single-process build, which the goldens come from) the diffusion limiter clamps every species-diffusion
+    flux to 0, so the fixtures above never see a non-zero one.  The reference's MPI build starts Dim_max at 1 (`-diffu-mpi=1`): that build cannot be
+    made here (no MPI), so this case is pinned against the oracle restatement only (same block of ConVenction_block.hpp:458-575, other branch):
+    5 steps, bit for bit, and the species-diffusion fluxes must have acted."""
+    import xfgpu
+    g = np.load(os.path.join(xfref.GOLDEN, "jet_w5_visc.npz"))   # (the jet: the shock-bubble preset sets Yil_limiter = 0, which switches the diffusion off by itself)
+    res = tuple(int(x) for x in g["res"])
+    from xfluids_b200 import host
+    out = {}
+    for mpi in (0, 1):
+        s = host.Setup(os.path.join(xfref.REPO, "settings", SETTINGS["jet"]), ["-run=%d,%d,%d" % res, "-weno=5", "-alpha=LLF", "-visc=1", "-diffu-mpi=%d" % mpi])
+        assert (s.transport.dim_max0 != 0.0) == bool(mpi)
+        eng = engine(s)
+        eng.set_state(g["ic_U"], g["ic_T"])
+        eng.boundary(eng.U, s.bc)
+        assert eng.update_states(eng.U) == 0
+        done, t, err = eng.run(s.bc, 5)
+        assert (done, err) == (5, 0)
+        out[mpi] = eng.download(eng.U)
+        eng.close()
+        if mpi:
+            o = xfref.Oracle("jet", res, weno=5, alpha=2, transport=s.transport)
+            o.set_state(g["ic_U"], g["ic_T"])
+            assert o.startup() == 0
+            n, dts, t_o = o.run(5)
+            assert n == 5 and t_o == t
+            assert np.array_equal(out[1], o.arr("U"))
+    assert not np.array_equal(out[0], out[1]), "the species-diffusion fluxes did not act"
