@@ -1,5 +1,5 @@
 """CPU, build container only: the oracle restatement against a live run of the compiled reference (oracle/_ref),
-100 steps of the 1-D multi-species shock tube and 20 steps of small SBI / jet / vortex grids.  Skipped where oracle/_ref
+100 steps of the 1-D multi-species shock tube and 20 steps of small SBI / jet / vortex grids (inviscid, CU6, limiter, viscous).  Skipped where oracle/_ref
 is absent.  Grid sizes are multiples of the reference work-group size (4): the reference's LU / RK-update kernels round
 their launch range up to the work-group size and only clip at Xmax/Ymax/Zmax, so with non-divisible sizes they also
 write a few max-side GHOST cells (overwritten by the next boundary fill) -- see DESIGN.md "quirks not reproduced"."""
@@ -35,6 +35,29 @@ def test_oracle_bitexact_vs_compiled_reference_cu6_and_positivity(case, res, wen
     A, meta, out = xfref.run_ref(case, res, nsteps, dump_steps=(nsteps,), weno=weno, stage_dump=True, pp=pp)
     assert "error=0" in out
     o = xfref.Oracle(case, res, weno=weno, pp=pp, cfl=xfref.PP_CFL if pp else None)
+    o.set_state(A["ic_U"], A["ic_T"])
+    o.startup()
+    n, dts, t = o.run(nsteps)
+    assert n == nsteps
+    assert np.array_equal(np.array(dts), np.array(meta["dt"]))
+    assert np.array_equal(o.arr("U"), A["U_step%d" % nsteps])
+    assert np.array_equal(o.arr("T"), A["T_step%d" % nsteps])
+
+
+@pytest.mark.parametrize("case,res,weno,alpha,pp,nsteps", [("sbi", (20, 12, 8), 5, 2, 0, 20), ("jet", (16, 12, 8), 5, 2, 0, 20), ("sbi", (20, 12, 8), 6, 3, 1, 12),
+                                                           ("sbi", (28, 16, 0), 5, 2, 0, 20)])
+def test_oracle_bitexact_vs_compiled_reference_viscous(case, res, weno, alpha, pp, nsteps):
+    """SURVEY 8 f3 on grids other than the golden ones: the viscous / heat-conduction / species-diffusion block of the oracle against live runs
+    of the reference built with Visc, Visc_Heat and Visc_Diffu (3-D, the shipped preset's CU6 + GLF + limiter set, and a 2-D block)."""
+    import os
+    from xfluids_b200 import host
+    if not xfref.ref_available(case, weno, alpha=alpha, pp=pp, visc=1):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    A, meta, out = xfref.run_ref(case, res, nsteps, dump_steps=(nsteps,), weno=weno, stage_dump=True, alpha=alpha, pp=pp, visc=1)
+    assert "error=0" in out
+    js = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json"}[case]
+    s = host.Setup(os.path.join(xfref.REPO, "settings", js), ["-run=%d,%d,%d" % res, "-visc=1"])
+    o = xfref.Oracle(case, res, weno=weno, alpha=alpha, pp=pp, cfl=xfref.PP_CFL if pp else None, transport=s.transport)
     o.set_state(A["ic_U"], A["ic_T"])
     o.startup()
     n, dts, t = o.run(nsteps)
