@@ -45,18 +45,21 @@ def test_oracle_bitexact_vs_compiled_reference_cu6_and_positivity(case, res, wen
 
 
 @pytest.mark.parametrize("case,res,weno,alpha,pp,nsteps", [("sbi", (20, 12, 8), 5, 2, 0, 20), ("jet", (16, 12, 8), 5, 2, 0, 20), ("sbi", (20, 12, 8), 6, 3, 1, 12),
-                                                           ("sbi", (28, 16, 0), 5, 2, 0, 20)])
+                                                           ("sbi", (28, 16, 0), 5, 2, 0, 20), ("shock-tube", (200, 0, 0), 5, 2, 0, 20)])
 def test_oracle_bitexact_vs_compiled_reference_viscous(case, res, weno, alpha, pp, nsteps):
     """SURVEY 8 f3 on grids other than the golden ones: the viscous / heat-conduction / species-diffusion block of the oracle against live runs
-    of the reference built with Visc, Visc_Heat and Visc_Diffu (3-D, the shipped preset's CU6 + GLF + limiter set, and a 2-D block)."""
+    of the reference built with Visc, Visc_Heat and Visc_Diffu (3-D, the shipped preset's CU6 + GLF + limiter set, a 2-D block and the 1-D shock tube)."""
     import os
     from xfluids_b200 import host
     if not xfref.ref_available(case, weno, alpha=alpha, pp=pp, visc=1):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     A, meta, out = xfref.run_ref(case, res, nsteps, dump_steps=(nsteps,), weno=weno, stage_dump=True, alpha=alpha, pp=pp, visc=1)
     assert "error=0" in out
-    js = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json"}[case]
+    js = {"sbi": "shock-bubble.json", "jet": "expanded-jet.json", "shock-tube": "1d-shock-tube.json"}[case]
     s = host.Setup(os.path.join(xfref.REPO, "settings", js), ["-run=%d,%d,%d" % res, "-visc=1"])
+    ns = s.num_species   # the host's transport fits are the reference's, bit for bit, for this mixture too (the shock tube adds AR)
+    for k, n in (("fit_visc", ns * 4), ("fit_therm", ns * 4), ("fit_Dkj", ns * ns * 4)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(s.transport, k), shape=(n,)), A[k]), k
     o = xfref.Oracle(case, res, weno=weno, alpha=alpha, pp=pp, cfl=xfref.PP_CFL if pp else None, transport=s.transport)
     o.set_state(A["ic_U"], A["ic_T"])
     o.startup()
