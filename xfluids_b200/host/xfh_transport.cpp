@@ -117,54 +117,43 @@ namespace xfh
 			std::ifstream fin(fpath);
 			if (!fin)
 				throw std::runtime_error("cannot open " + fpath);
-			for (int n = 0; n < 8; n++)
-				fin >> delta_star[n];
-			for (int i = 0; i < 37; i++)
+			// file order: the 8 reduced dipole moments; 37 rows of {T*, Omega(2,2)* at the 8 moments}; 37 x 8 values of Omega(1,1)*
+			auto take = [&](double *dst, int count)
 			{
-				fin >> T_star[i];
-				for (int j = 0; j < 8; j++)
-					fin >> Omega_table[1][i][j];
-			}
-			for (int p = 0; p < 37; p++)
-				for (int q = 0; q < 8; q++)
-					fin >> Omega_table[0][p][q];
+				for (int c = 0; c < count; c++)
+					fin >> dst[c];
+			};
+			take(delta_star, 8);
+			for (int row = 0; row < 37; row++)
+				take(T_star + row, 1), take(mem + (37 + row) * 8, 8); // table index 1 = Omega(2,2)*
+			take(mem, 37 * 8);                                        // table index 0 = Omega(1,1)*
 			if (!fin)
 				throw std::runtime_error("collision_integral.dat: short table");
 		}
 		double Omega_interpolated(double Tstar, double deltastar, int index) const
 		{
-			int ti1 = 0, ti2 = 1, ti3 = 2;
-			if (Tstar > T_star[0] && Tstar < T_star[36])
+			// first of the three consecutive nodes the reference's branches pick (viscfit.cpp:366-420): clamped at both ends, otherwise the
+			// node below x and the two after it -- for x between the last two nodes that is one node PAST the grid (see the note above)
+			auto first_node = [](const double *grid, int n, double x)
 			{
-				int ii = 1;
-				while (Tstar > T_star[ii])
-					ii = ii + 1;
-				ti1 = ii - 1, ti2 = ii, ti3 = ii + 1;
+				if (x <= grid[0])
+					return 0;
+				if (x >= grid[n - 1])
+					return n - 3;
+				int at = 1;
+				while (x > grid[at])
+					++at;
+				return at - 1;
+			};
+			const int ti = first_node(T_star, 37, Tstar), tj = first_node(delta_star, 8, deltastar);
+			double aa[3], col[3];
+			for (int c = 0; c < 3; c++)
+			{ // quadratic through the three T* nodes at each of the three delta* nodes, evaluated at T*
+				GetQuadraticInterCoeff(T_star[ti], T_star[ti + 1], T_star[ti + 2], Omega_table[index][ti][tj + c], Omega_table[index][ti + 1][tj + c],
+									   Omega_table[index][ti + 2][tj + c], aa);
+				col[c] = aa[0] + aa[1] * Tstar + aa[2] * Tstar * Tstar;
 			}
-			else if (Tstar <= T_star[0])
-				ti1 = 0, ti2 = 1, ti3 = 2;
-			else if (Tstar >= T_star[36])
-				ti1 = 34, ti2 = 35, ti3 = 36;
-			int tj1 = 0, tj2 = 1, tj3 = 2;
-			if (deltastar > delta_star[0] && deltastar < delta_star[7])
-			{
-				int jj = 1;
-				while (deltastar > delta_star[jj])
-					jj = jj + 1;
-				tj1 = jj - 1, tj2 = jj, tj3 = jj + 1;
-			}
-			else if (deltastar <= delta_star[0])
-				tj1 = 0, tj2 = 1, tj3 = 2;
-			else if (deltastar >= delta_star[7])
-				tj1 = 5, tj2 = 6, tj3 = 7;
-			double aa[3];
-			GetQuadraticInterCoeff(T_star[ti1], T_star[ti2], T_star[ti3], Omega_table[index][ti1][tj1], Omega_table[index][ti2][tj1], Omega_table[index][ti3][tj1], aa);
-			const double temp1 = aa[0] + aa[1] * Tstar + aa[2] * Tstar * Tstar;
-			GetQuadraticInterCoeff(T_star[ti1], T_star[ti2], T_star[ti3], Omega_table[index][ti1][tj2], Omega_table[index][ti2][tj2], Omega_table[index][ti3][tj2], aa);
-			const double temp2 = aa[0] + aa[1] * Tstar + aa[2] * Tstar * Tstar;
-			GetQuadraticInterCoeff(T_star[ti1], T_star[ti2], T_star[ti3], Omega_table[index][ti1][tj3], Omega_table[index][ti2][tj3], Omega_table[index][ti3][tj3], aa);
-			const double temp3 = aa[0] + aa[1] * Tstar + aa[2] * Tstar * Tstar;
-			GetQuadraticInterCoeff(delta_star[tj1], delta_star[tj2], delta_star[tj3], temp1, temp2, temp3, aa);
+			GetQuadraticInterCoeff(delta_star[tj], delta_star[tj + 1], delta_star[tj + 2], col[0], col[1], col[2], aa);
 			return aa[0] + aa[1] * deltastar + aa[2] * deltastar * deltastar;
 		}
 		double viscosity(const double *specie, double T) const
