@@ -22,64 +22,60 @@ namespace xfh
 		const double universal_gas_const = 6.02214076e26 * 1.380649e-23;
 		enum { geo = 0, epsilon_kB = 1, d_ = 2, mue = 3, alpha = 4, Zrot_298 = 5, WI = 6, SID = 8 };
 
-		void GetQuadraticInterCoeff(double x1, double x2, double x3, double f1, double f2, double f3, double *aa)
+		// parabola q[0] + q[1] x + q[2] x^2 through three nodes (mixture.hpp:70-77), divided differences in the reference's order
+		void GetQuadraticInterCoeff(double xa, double xb, double xc, double fa, double fb, double fc, double *q)
 		{
-			aa[2] = ((f1 - f2) / (x1 - x2) - (f2 - f3) / (x2 - x3)) / (x1 - x3);
-			aa[1] = (f1 - f2) / (x1 - x2) - aa[2] * (x1 + x2);
-			aa[0] = f1 - aa[1] * x1 - aa[2] * x1 * x1;
+			q[2] = ((fa - fb) / (xa - xb) - (fb - fc) / (xb - xc)) / (xa - xc);
+			q[1] = (fa - fb) / (xa - xb) - q[2] * (xa + xb);
+			q[0] = fa - q[1] * xa - q[2] * xa * xa;
 		}
 		double ZrotFunc(double x) { return 1.0 + std::sqrt(pi * x) * pi / 2.0 + x * (0.25 * pi * pi + 2.0) + std::pow(pi * x, 1.5); }
 
-		// normal equations + Cholesky (mixture.hpp:89-150)
-		void Solve_Overdeter_equations(const std::vector<std::array<double, 4>> &AA, const std::vector<double> &b, double *xx)
+		// Least squares through the normal equations, solved by Cholesky: G = A^T A = L L^T, then L y = A^T b and L^T c = y.  Every sum and
+		// every quotient runs in the order of the reference's solver (mixture.hpp:89-150): the fits have to come out bit for bit.
+		void Solve_Overdeter_equations(const std::vector<std::array<double, 4>> &A, const std::vector<double> &b, double *coef)
 		{
-			const int nn = 4, mm = int(b.size());
-			double CC[4][4], dd[4];
-			for (int i = 0; i < nn; i++)
+			constexpr int N = 4;
+			const size_t rows = b.size();
+			double G[N][N] = {}, rhs[N] = {}, y[N];
+			for (int c = 0; c < N; c++)
 			{
-				dd[i] = 0.0;
-				for (int j = 0; j < nn; j++)
-					CC[i][j] = 0.0;
+				for (size_t r = 0; r < rows; r++)
+					rhs[c] += A[r][c] * b[r];
+				for (int c2 = 0; c2 < N; c2++)
+					for (size_t r = 0; r < rows; r++)
+						G[c][c2] += A[r][c] * A[r][c2];
 			}
-			for (int i = 0; i < nn; i++)
+			// L overwrites the lower triangle of G, column by column
+			G[0][0] = std::sqrt(G[0][0]);
+			for (int r = 1; r < N; r++)
+				G[r][0] /= G[0][0];
+			for (int d = 1; d < N; d++)
 			{
-				for (int q = 0; q < mm; q++)
-					dd[i] = dd[i] + AA[q][i] * b[q];
-				for (int j = 0; j < nn; j++)
-					for (int k = 0; k < mm; k++)
-						CC[i][j] = CC[i][j] + AA[k][i] * AA[k][j];
-			}
-			CC[0][0] = std::sqrt(CC[0][0]);
-			for (int p = 1; p < nn; p++)
-				CC[p][0] = CC[p][0] / CC[0][0];
-			for (int k = 1; k < nn; k++)
-			{
-				for (int m = 0; m < k; m++)
-					CC[k][k] = CC[k][k] - CC[k][m] * CC[k][m];
-				CC[k][k] = std::sqrt(CC[k][k]);
-				for (int i = k + 1; i < nn; i++)
+				for (int m = 0; m < d; m++)
+					G[d][d] -= G[d][m] * G[d][m];
+				G[d][d] = std::sqrt(G[d][d]);
+				for (int r = d + 1; r < N; r++)
 				{
-					for (int m = 0; m < k; m++)
-						CC[i][k] = CC[i][k] - CC[i][m] * CC[k][m];
-					CC[i][k] = CC[i][k] / CC[k][k];
+					for (int m = 0; m < d; m++)
+						G[r][d] -= G[r][m] * G[d][m];
+					G[r][d] /= G[d][d];
 				}
 			}
-			xx[0] = dd[0] / CC[0][0];
-			for (int j = 1; j < nn; j++)
+			y[0] = rhs[0] / G[0][0]; // forward substitution
+			for (int r = 1; r < N; r++)
 			{
-				for (int q = 0; q < j; q++)
-					dd[j] = dd[j] - CC[j][q] * xx[q];
-				xx[j] = dd[j] / CC[j][j];
+				for (int m = 0; m < r; m++)
+					rhs[r] -= G[r][m] * y[m];
+				y[r] = rhs[r] / G[r][r];
 			}
-			dd[nn - 1] = xx[nn - 1] / CC[nn - 1][nn - 1];
-			for (int i = nn - 2; i >= 0; i--)
+			coef[N - 1] = y[N - 1] / G[N - 1][N - 1]; // back substitution, highest coefficient first
+			for (int r = N - 2; r >= 0; r--)
 			{
-				for (int p = nn - 1; p > i; p--)
-					xx[i] = xx[i] - CC[p][i] * dd[p];
-				dd[i] = xx[i] / CC[i][i];
+				for (int m = N - 1; m > r; m--)
+					y[r] -= G[m][r] * coef[m];
+				coef[r] = y[r] / G[r][r];
 			}
-			for (int m = 0; m < nn; m++)
-				xx[m] = dd[m];
 		}
 	} // namespace
 
